@@ -1,0 +1,184 @@
+/*
+ * mmif_b200.h — C ABI of libmmif_b200.so: the fusion objective (reference core/loss.py)
+ * and the objective metric suite (reference core/metric.py) as sm_100a CUDA kernels.
+ *
+ * The reference repository is pure Python and has no FFI; the boundary it defines is the
+ * Python call surface (core/loss.py:16-19, core/metric.py:16-21).  Every entry point below
+ * names the reference function(s) it replaces.  The Python mirror of that surface
+ * (multi-modal-image-fusion_b200/core/{loss,metric}.py) binds these symbols with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every image pointer is DEVICE memory, dense row-major
+ *     float32 [N][H][W] (the reference's (N,1,H,W) tensors, C == 1);
+ *   - return 0 on success, negative MMIF_E_* on error; mmif_last_error() gives the text for the
+ *     calling thread; no exception, abort or device synchronisation crosses the ABI;
+ *   - the caller owns every buffer, including the workspace `ws` (size from the matching
+ *     *_workspace_bytes call; must be zero-filled once before first use — the kernels leave it
+ *     zeroed again); the library never allocates or frees device memory;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and results stay on the
+ *     device; re-entrant (no mutable globals besides __constant__ tap tables written per launch
+ *     configuration under a mutex).
+ */
+#ifndef MMIF_B200_H_
+#define MMIF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMIF_VERSION 100 /* 0.1.0 */
+
+enum {
+    MMIF_OK = 0,
+    MMIF_E_NULL = -1,        /* null pointer argument */
+    MMIF_E_SHAPE = -2,       /* unsupported shape (e.g. H or W smaller than the window) */
+    MMIF_E_MODE = -3,        /* unsupported mode / configuration value */
+    MMIF_E_WORKSPACE = -4,   /* workspace too small */
+    MMIF_E_ALIGN = -5,       /* pointer not 4-byte aligned */
+    MMIF_E_CUDA = -6,        /* a CUDA runtime call failed (text in mmif_last_error) */
+    MMIF_E_DEVICE = -7       /* not an sm_100 device / no device */
+};
+
+enum { MMIF_COMBINE_MAX = 0, MMIF_COMBINE_AVG = 1 };   /* PixelLoss/GradLoss forward(mode=) loss.py:294-304,330-344 */
+enum { MMIF_NORM_L1 = 1, MMIF_NORM_L2 = 2 };           /* NormLoss mode, loss.py:375-385 */
+
+/* Configuration of the three-term objective as train.py:302-317 wires it. */
+typedef struct MmifLossCfg {
+    float w_ssim;       /* SSIMLoss weight   (train.py:306, 1.0)  */
+    float w_pixel;      /* PixelLoss weight  (train.py:307, 0.01) */
+    float w_grad;       /* GradLoss weight   (train.py:308, 0.1)  */
+    float data_range;   /* L of C1=(0.01L)^2, C2=(0.03L)^2 (loss.py:91-93); SSIMLoss default 1.0 */
+    int32_t pixel_combine; /* MMIF_COMBINE_*  */
+    int32_t grad_combine;  /* MMIF_COMBINE_*  */
+    int32_t pixel_norm;    /* MMIF_NORM_*     */
+    int32_t grad_norm;     /* MMIF_NORM_*     */
+    int32_t want_grad;     /* fwd only: !=0 -> also write d(total)/d(imgf) for unit upstream
+                              gradients into `dF_unit` (single-pass variant), else ignored */
+    int32_t reserved;
+} MmifLossCfg;
+
+/* Layout of the double[] written by mmif_fusion_loss_fwd (device memory). */
+enum {
+    MMIF_LOSS_SSIM = 0,   /* w_ssim * (1 - (mean_b ssim(I1,If) + mean_b ssim(I2,If))/2)   SSIMLoss('ssim') loss.py:253-257,284 */
+    MMIF_LOSS_PIXEL = 1,  /* PixelLoss value                                               loss.py:294-304 */
+    MMIF_LOSS_GRAD = 2,   /* GradLoss value                                                loss.py:330-344 */
+    MMIF_LOSS_TOTAL = 3,  /* sum of the three (train.py:69) */
+    MMIF_LOSS_HEAD = 4,   /* per-sample block starts here: B x MMIF_LOSS_PER_SAMPLE */
+    MMIF_LOSS_PER_SAMPLE = 6 /* ssim1, cs1, sigma1, ssim2, cs2, sigma2 — the dict of SSIM.forward (loss.py:105-110) */
+};
+
+int mmif_version(void);
+const char* mmif_last_error(void);
+/* 0 if device `dev` is usable by this library (compute capability 10.x). */
+int mmif_check_device(int dev);
+/* Register the reference's own 1-D Gaussian taps for (win, sigma): `taps` = win HOST floats, i.e.
+ * _gaussian_kernel(win, sigma) of loss.py:24-30 / metric.py:290-296 evaluated by the caller with
+ * the reference's torch ops.  Optional: without it the library builds the table itself (float32
+ * taps normalised by a sequentially accumulated float32 sum), which can differ from torch's table
+ * in the last bit of the normalisation.  win <= 17.  Thread-safe; affects later launches. */
+int mmif_set_gaussian_taps(int win, double sigma, const float* taps);
+
+/* ---------------------------------------------------------------- fusion objective ------- */
+size_t mmif_loss_workspace_bytes(int B, int H, int W);
+size_t mmif_loss_out_doubles(int B);
+
+/* Replaces SSIMLoss('ssim').forward + PixelLoss.forward + GradLoss.forward (loss.py:252-257,
+ * 294-304, 330-344) and the SSIM.forward dict (loss.py:179-185) in one launch.
+ * i1,i2,f: [B][H][W]; out: mmif_loss_out_doubles(B) doubles; dF_unit: [B][H][W] or NULL. */
+int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
+                         const MmifLossCfg* cfg, double* out, float* dF_unit,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces autograd's backward of the three modules w.r.t. imgf (train.py:71): recomputes the
+ * stencil and writes dF = g[0]*dLssim/dIf + g[1]*dLpixel/dIf + g[2]*dLgrad/dIf.
+ * gout3: 3 floats in DEVICE memory (upstream gradients of the three loss values). */
+int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
+                         const MmifLossCfg* cfg, const float* gout3, float* dF,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* TVLoss.forward (loss.py:347-358) on x [N][H][W]: out[0] = w*(norm(dv) + norm(dh)). */
+int mmif_tv_loss(const float* x, int N, int H, int W, int norm, float weight, double* out,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- metric suite ----------- */
+/* All metric entries are batched over N independent pairs (a[n], b[n], f[n]) of one shape and
+ * write doubles per pair.  ws from mmif_metric_workspace_bytes. */
+size_t mmif_metric_workspace_bytes(int N, int H, int W);
+
+enum { /* mmif_stats output, per pair */
+    MMIF_ST_MEAN_F = 0, /* calc_mean(f)   metric.py:25-26 */
+    MMIF_ST_SD = 1,     /* calc_std(f)    metric.py:30-34 */
+    MMIF_ST_AG = 2,     /* calc_ag(f)     metric.py:38-46 */
+    MMIF_ST_SF = 3,     /* calc_sf(f)     metric.py:50-59 */
+    MMIF_ST_MSE_AF = 4, /* calc_mse(a,f)  metric.py:63-68 */
+    MMIF_ST_MSE_BF = 5,
+    MMIF_ST_CC_AF = 6,  /* calc_cc(a,f)   metric.py:80-91 */
+    MMIF_ST_CC_BF = 7,
+    MMIF_ST_SCD = 8,    /* calc_scd(a,b,f) metric.py:95-99 */
+    MMIF_ST_MEAN_A = 9, MMIF_ST_MEAN_B = 10, MMIF_ST_SD_A = 11, MMIF_ST_SD_B = 12,
+    MMIF_ST_CC_AB = 13,
+    MMIF_ST_COUNT = 16
+};
+int mmif_stats(const float* a, const float* b, const float* f, int N, int H, int W, double* out,
+               void* ws, size_t ws_bytes, void* stream);
+
+enum { /* mmif_hist entropy outputs, per pair */
+    MMIF_EN_A = 0, MMIF_EN_B = 1, MMIF_EN_F = 2, /* calc_entropy      metric.py:119-125 (float32 arithmetic) */
+    MMIF_JE_AF = 3, MMIF_JE_BF = 4,              /* calc_joint_ent    metric.py:148-154 (float64) */
+    MMIF_CE_AF = 5, MMIF_CE_BF = 6,              /* calc_cross_ent    metric.py:158-165 (float32 arithmetic) */
+    MMIF_MI_AF = 7, MMIF_MI_BF = 8,              /* calc_mul_info     metric.py:169-188, normalized=False */
+    MMIF_NMI_AF = 9, MMIF_NMI_BF = 10,           /* calc_mul_info(normalized=True) */
+    MMIF_EN_COUNT = 12
+};
+#define MMIF_HIST_WORDS (3 * 256 + 2 * 65536)
+/* Replaces calc_prob/calc_joint_prob histogramming (torch.histc metric.py:113, np.histogram2d
+ * metric.py:141-143) and the entropy family.  counts: per pair MMIF_HIST_WORDS uint32
+ * [hist_a 256 | hist_b 256 | hist_f 256 | joint_af 256x256 (row = a bin) | joint_bf 256x256];
+ * must be zero-filled by the caller.  ent: per pair MMIF_EN_COUNT doubles (may be NULL). */
+int mmif_hist(const float* a, const float* b, const float* f, int N, int H, int W,
+              uint32_t* counts, double* ent, void* ws, size_t ws_bytes, void* stream);
+
+/* calc_Qabf(a,b,f,L,full=True) (metric.py:233-256) -> per pair 4 doubles:
+ * qabf, nabf (modified), labf, nabf_unmodified (calc_Nabf(modified=False), metric.py:273). */
+int mmif_qabf(const float* a, const float* b, const float* f, int N, int H, int W, float L,
+              double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* calc_ssim(x,f,win,data_range,use_padding,full=True) (metric.py:316-364) for the two pairs
+ * (a,f) and (b,f) -> per pair 4 doubles: ssim_af, cs_af, ssim_bf, cs_bf (global means). */
+int mmif_ssim(const float* a, const float* b, const float* f, int N, int H, int W, int win_size,
+              float data_range, int use_padding, double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* calc_msssim (metric.py:368-402) for (a,f) and (b,f) -> per pair 2 + 5*4 doubles:
+ * msssim_af, msssim_bf, then per level ssim_af, cs_af, ssim_bf, cs_bf. */
+#define MMIF_MSSSIM_DOUBLES 22
+int mmif_msssim(const float* a, const float* b, const float* f, int N, int H, int W, int win_size,
+                float data_range, double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* calc_vif + calc_viff (metric.py:406-491) -> per pair 2 + 4*6 doubles: viff(simple=False),
+ * viff(simple=True), then per scale sum num1, den1, num2, den2, num_sel, den_sel. */
+#define MMIF_VIFF_DOUBLES 26
+int mmif_viff(const float* a, const float* b, const float* f, int N, int H, int W, double* out,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* The 16-metric row of eval.py:29-75 for N pairs -> per pair 16 doubles in eval.py order:
+ * sd ag sf mse psnr cc scd en ce mi qabf nabf labf ssim msssim viff. */
+#define MMIF_EVAL_METRICS 16
+int mmif_eval_suite(const float* a, const float* b, const float* f, int N, int H, int W,
+                    double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* Host-buffer convenience used by the end-to-end benchmark and by CPU-tensor callers
+ * (eval.py:198-206 leaves its tensors on the host): copies the three host images to the
+ * device scratch `dev_scratch` (3*N*H*W floats), runs mmif_eval_suite and copies the row back.
+ * Synchronises `stream` before returning. */
+int mmif_eval_suite_host(const float* a_host, const float* b_host, const float* f_host, int N, int H,
+                         int W, double* out_host, float* dev_scratch, double* dev_out,
+                         void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMIF_B200_H_ */

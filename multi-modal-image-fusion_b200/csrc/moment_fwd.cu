@@ -1,0 +1,85 @@
+// Instantiations and host launcher of the forward strip-streaming kernel.
+#include "moment_fwd.cuh"
+
+namespace mmif {
+
+int fwd_seg_rows(int rows, int other_ctas) {
+    // largest segment (fewest halo rows) that still gives >= 2 CTAs per SM
+    const int target = 2 * 148;
+    int s = 256;
+    while (s > 16 && (long long)other_ctas * ceil_div(rows, s) < target) s >>= 1;
+    return s;
+}
+
+static int two_of(int win) { return ((kTWI - (win - 1)) / 4) * 4; }
+
+struct Geo { int Hout, Wout, nstrip, seg_rows, nseg; };
+static Geo geo_of(int win, int B, int H, int W) {
+    Geo g;
+    g.Hout = H - (win - 1); g.Wout = W - (win - 1);
+    g.nstrip = ceil_div(g.Wout, two_of(win));
+    g.seg_rows = fwd_seg_rows(g.Hout, B * g.nstrip);
+    g.nseg = ceil_div(g.Hout, g.seg_rows);
+    return g;
+}
+
+size_t fwd_ws_bytes(int win, int B, int H, int W) {
+    if (B < 1 || H < win || W < win) return 0;
+    const Geo g = geo_of(win, B, H, W);
+    return ws_counters_bytes(B) + (size_t)B * g.nstrip * g.nseg * 8 * sizeof(double);
+}
+
+template <int WIN, int EPI>
+static int launch_t(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& my, const FwdParams& p, dim3 grid,
+                    cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMIF_CUDA(cudaFuncSetAttribute(moment_fwd_kernel<WIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_done = true;
+    }
+    moment_fwd_kernel<WIN, EPI><<<grid, kNT, sizeof(Smem), st>>>(m1, m2, my, p);
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
+}
+
+int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, const float* y, int B, int H, int W,
+                      double* sums, long long sums_stride, double* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t need = fwd_ws_bytes(L.win, B, H, W);
+    if (need == 0) { set_error("shape (%d,%d,%d) smaller than the %d-tap window", B, H, W, L.win); return MMIF_E_SHAPE; }
+    if (!ws || ws_bytes < need) { set_error("workspace too small: %zu < %zu", ws_bytes, need); return MMIF_E_WORKSPACE; }
+    const Geo g = geo_of(L.win, B, H, W);
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.x1 = x1; p.x2 = x2; p.y = y;
+    p.B = B; p.H = H; p.W = W; p.Hout = g.Hout; p.Wout = g.Wout;
+    p.seg_rows = g.seg_rows; p.nseg = g.nseg; p.nstrip = g.nstrip;
+    make_taps(&p.taps, L.win, L.sigma);
+    const double R = L.data_range;
+    p.C1 = (float)((0.01 * R) * (0.01 * R)); p.C2 = (float)((0.03 * R) * (0.03 * R));
+    p.pixel_combine = L.cfg.pixel_combine; p.grad_combine = L.cfg.grad_combine;
+    p.pixel_norm = L.cfg.pixel_norm; p.grad_norm = L.cfg.grad_norm;
+    p.w_ssim = L.cfg.w_ssim; p.w_pixel = L.cfg.w_pixel; p.w_grad = L.cfg.w_grad;
+    p.do_sobel = L.do_sobel; p.finalize = L.finalize;
+    unsigned char* w8 = (unsigned char*)ws;
+    p.counters = (unsigned*)w8;
+    p.partial = (double*)(w8 + ws_counters_bytes(B));
+    p.sums = sums; p.sums_stride = sums_stride; p.out = out;
+    CUtensorMap m1, m2, my;
+    p.use_tma = make_tensor_map(&m1, x1, B, H, W, kTWI, kRB) && make_tensor_map(&m2, x2, B, H, W, kTWI, kRB) &&
+                make_tensor_map(&my, y, B, H, W, kTWI, kRB);
+    if (!p.use_tma) { memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2)); memset(&my, 0, sizeof(my)); }
+    dim3 grid(g.nstrip, g.nseg, B);
+    if (L.epi == EPI_SSIM && L.win == 11) return launch_t<11, EPI_SSIM>(m1, m2, my, p, grid, st);
+    if (L.epi == EPI_VIF) {
+        switch (L.win) {
+            case 17: return launch_t<17, EPI_VIF>(m1, m2, my, p, grid, st);
+            case 9: return launch_t<9, EPI_VIF>(m1, m2, my, p, grid, st);
+            case 5: return launch_t<5, EPI_VIF>(m1, m2, my, p, grid, st);
+            case 3: return launch_t<3, EPI_VIF>(m1, m2, my, p, grid, st);
+        }
+    }
+    set_error("no kernel instantiated for window %d / epilogue %d", L.win, L.epi);
+    return MMIF_E_MODE;
+}
+
+}  // namespace mmif

@@ -1,0 +1,266 @@
+// Forward strip-streaming kernel over the engine of stencil.cuh, templated on the window size and
+// on the per-window epilogue:
+//   EPI_SSIM : SSIM / CS / clamped-variance sums of the pairs (x1,y), (x2,y)  [+ optional Sobel and
+//              pixel terms of the fusion objective, loss.py:294-344]
+//   EPI_VIF  : VIF numerator / denominator sums of the pairs and of the gain-selected source
+//              (metric.py:436-456, 486-489)
+// Reads x1, x2, y once (12 B/pixel) and writes only per-CTA partial sums; the last CTA of each sample
+// reduces that sample's partials in a fixed order, and (FIN_LOSS) the last sample-finisher writes the
+// loss scalars — one launch, deterministic, no float atomics.
+#pragma once
+#include "stencil.cuh"
+
+namespace mmif {
+
+enum { EPI_SSIM = 0, EPI_VIF = 1 };
+enum { FIN_SUMS = 0, FIN_LOSS = 1 };
+
+// TMA needs the global address of a box (innermost coordinate * 4 B) 16-byte aligned, so strips
+// advance by a multiple of 4 columns.
+template <int WIN>
+struct FwdGeo {
+    static constexpr int HALO = WIN - 1;
+    static constexpr int TWO = ((kTWI - HALO) / 4) * 4;   // output columns per strip
+};
+
+struct FwdParams {
+    const float* x1; const float* x2; const float* y;
+    int B, H, W, Hout, Wout;
+    int seg_rows, nseg, nstrip;
+    Taps taps;
+    float C1, C2;
+    int pixel_combine, grad_combine, pixel_norm, grad_norm;
+    float w_ssim, w_pixel, w_grad;
+    int use_tma;
+    int do_sobel;            // EPI_SSIM only: also accumulate the Sobel / pixel terms
+    int finalize;            // FIN_SUMS / FIN_LOSS
+    unsigned* counters;      // [B+1], zero on entry, left zero
+    double* partial;         // [B][nblk][8]
+    double* sums;            // per-sample raw sums: sums[n*sums_stride + 0..7]
+    long long sums_stride;
+    double* out;             // FIN_LOSS: loss block (mmif_b200.h MMIF_LOSS_*)
+};
+
+static inline size_t ws_counters_bytes(int B) { return (size_t)(((B + 1) * 4 + 255) / 256) * 256; }
+
+// --- forward Sobel / pixel terms for the pixel rows a batch owns (thread = column) ----------
+__device__ __forceinline__ void fwd_sobel_pixel(const Smem& sm, const FwdParams& p, int i0, int j0, int rlo, int rhi, int clo,
+                                                int chi, float& pix_sum, float& grad_sum) {
+    const int c = j0 + (int)threadIdx.x;
+    if (c < clo || c >= chi) return;
+    const int t0 = threadIdx.x;
+    const int tm = ((c == 0) ? 1 : c - 1) - j0;
+    const int tp = ((c == p.W - 1) ? p.W - 2 : c + 1) - j0;
+    float dA[3], dB[3], sA[3], sB[3], u0p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dA[k] = dB[k] = sA[k] = sB[k] = u0p[k] = 0.f;
+    for (int r = rlo - 1; r <= rhi; ++r) {
+        const int rr = (r < 0) ? -r : ((r >= p.H) ? 2 * p.H - 2 - r : r);
+        const int lr = (rr - i0) & (kRingRows - 1);
+        float S[3], u0[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float um = sm.ring[k][lr][tm];
+            const float uc = sm.ring[k][lr][t0];
+            const float up = sm.ring[k][lr][tp];
+            const float d = up - um;
+            const float s = um + 2.f * uc + up;
+            const float gx = dA[k] + 2.f * dB[k] + d;
+            const float gy = s - sA[k];
+            S[k] = fabsf(gx) + fabsf(gy);
+            dA[k] = dB[k]; dB[k] = d; sA[k] = sB[k]; sB[k] = s;
+            u0[k] = u0p[k]; u0p[k] = uc;        // u0 = centre value of row r-1
+        }
+        if (r >= rlo + 1) {                      // S[] / u0[] now describe pixel row r-1
+            if (p.grad_combine == MMIF_COMBINE_MAX) {
+                grad_sum += norm_val(S[2] - fmaxf(S[0], S[1]), p.grad_norm);
+            } else {
+                grad_sum += 0.5f * (norm_val(S[2] - S[0], p.grad_norm) + norm_val(S[2] - S[1], p.grad_norm));
+            }
+            if (p.pixel_combine == MMIF_COMBINE_MAX) {
+                pix_sum += norm_val(u0[2] - fmaxf(u0[0], u0[1]), p.pixel_norm);
+            } else {
+                pix_sum += 0.5f * (norm_val(u0[2] - u0[0], p.pixel_norm) + norm_val(u0[2] - u0[1], p.pixel_norm));
+            }
+        }
+    }
+}
+
+// log2(1+x), accurate for small x (the reference's fp32 log2(1 + x) loses x's low bits; its fp64
+// evaluation does not — stay near the fp64 value).
+__device__ __forceinline__ float log2_1p(float x) { return log1pf(x) * 1.4426950408889634f; }
+
+template <int WIN, int EPI>
+__global__ void __launch_bounds__(kNT, 2)
+moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                  const __grid_constant__ CUtensorMap mapy, const FwdParams p) {
+    constexpr int HALO = FwdGeo<WIN>::HALO;
+    constexpr int TWO = FwdGeo<WIN>::TWO;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int strip = blockIdx.x, seg = blockIdx.y, n = blockIdx.z;
+    const int j0 = strip * TWO, i0 = seg * p.seg_rows;
+    const int rows_out = min(p.seg_rows, p.Hout - i0);
+    const int cols_out = min(TWO, p.Wout - j0);
+    const int nb = (rows_out + kRB - 1) / kRB;
+    const size_t img_off = (size_t)n * p.H * p.W;
+
+    RingSrc src;
+    src.img[0] = p.x1 + img_off; src.img[1] = p.x2 + img_off; src.img[2] = p.y + img_off;
+    src.H = p.H; src.W = p.W; src.row0 = i0; src.col0 = j0; src.n = n; src.use_tma = p.use_tma != 0;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mbar_init((uint64_t*)&sm.mbar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const Shift sh = tile_shift(src.img[0], src.img[1], src.img[2], p.H, p.W, i0 + p.seg_rows / 2 + HALO / 2, j0 + kTWI / 2, p.taps);
+
+    ring_issue(sm, src, &map1, &map2, &mapy, 0);
+    ring_issue(sm, src, &map1, &map2, &mapy, 1);
+    ring_issue(sm, src, &map1, &map2, &mapy, 2);
+    __syncthreads();
+    ring_wait(sm, src, 0);
+    ring_wait(sm, src, 1);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ho = lane & 7, hg = warp * 4 + (lane >> 3);
+    float2 s0 = f2(0.f, 0.f), s1 = f2(0.f, 0.f), s2 = f2(0.f, 0.f);   // three packed running sums
+    float pix_sum = 0.f, grad_sum = 0.f;
+    const int clo = (strip == 0) ? 0 : j0 + HALO / 2;
+    const int chi = (strip == p.nstrip - 1) ? p.W : j0 + TWO + HALO / 2;
+    constexpr float kVifEps = 1e-10f, kVifNoise = 325.125f;            // metric.py:407-408
+
+    for (int b = 0; b < nb; ++b) {
+        ring_wait(sm, src, b + 2);
+        if (b + 1 < nb) ring_issue(sm, src, &map1, &map2, &mapy, b + 3);
+        vpass_moments<WIN>(sm, p.taps, sh, (b & 3) * kRB);
+        if (EPI == EPI_SSIM && p.do_sobel) {
+            const int rlo = (seg == 0 && b == 0) ? 0 : i0 + b * kRB + HALO / 2;
+            const int rhi = (seg == p.nseg - 1 && b == nb - 1) ? p.H : i0 + b * kRB + kRB + HALO / 2;
+            fwd_sobel_pixel(sm, p, i0, j0, rlo, rhi, clo, chi, pix_sum, grad_sum);
+        }
+        __syncthreads();
+        const int rows_b = min(kRB, rows_out - b * kRB);
+        if (ho < rows_b && hg * 8 < cols_out) {
+            float2 acc[8][4];
+            hpass<WIN, 4, false>(sm.vbuf + ho * kVPitch + hg * 8, kVCols, p.taps, acc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (hg * 8 + j < cols_out) {
+                    const Stats st = stats_from(moments_of(acc[j]), sh);
+                    const float2 vk = max2(st.vk, 0.f);
+                    const float vy = fmaxf(st.vy, 0.f);
+                    if (EPI == EPI_SSIM) {
+                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
+                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
+                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
+                        const float2 B2 = add2(vk, bcast(vy + p.C2));
+                        s0 = add2(s0, fdiv_nr2(mul2(A1, A2), mul2(B1, B2)));
+                        s1 = add2(s1, fdiv_nr2(A2, B2));
+                        s2 = add2(s2, max2(vk, 1e-4f));
+                    } else {
+                        float num[2], den[2], gg[2];
+                        const float v1[2] = {vk.x, vk.y}, c12[2] = {st.cov.x, st.cov.y};
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            float sig1 = v1[k];
+                            float g = __fdiv_rn(c12[k], sig1 + kVifEps);
+                            float sv = vy - g * c12[k];
+                            if (sig1 < kVifEps) { g = 0.f; sv = vy; sig1 = 0.f; }
+                            if (vy < kVifEps) { g = 0.f; sv = 0.f; }
+                            if (g < 0.f) { sv = vy; g = 0.f; }
+                            if (sv < kVifEps) sv = kVifEps;
+                            num[k] = log2_1p(__fdiv_rn(g * g * sig1, sv + kVifNoise));
+                            den[k] = log2_1p(sig1 * (1.0f / kVifNoise));
+                            gg[k] = g;
+                        }
+                        const bool pick1 = gg[0] < gg[1];
+                        s0 = add2(s0, f2(num[0], den[0]));
+                        s1 = add2(s1, f2(num[1], den[1]));
+                        s2 = add2(s2, pick1 ? f2(num[0], den[0]) : f2(num[1], den[1]));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per-CTA partial, then deterministic per-sample / global finish by the last arrivals ----
+    // SSIM: [ssim1, ssim2, cs1, cs2, sig1, sig2, pix, grad]; VIF: [num1, den1, num2, den2, numsel, densel, 0, 0]
+    double v[8] = {(double)s0.x, (double)s0.y, (double)s1.x, (double)s1.y, (double)s2.x, (double)s2.y,
+                   (double)pix_sum, (double)grad_sum};
+    block_sum<8, kNT>(v, sm.red);
+    const int nblk = p.nstrip * p.nseg;
+    const int blk = seg * p.nstrip + strip;
+    if (threadIdx.x == 0) {
+        double* dst = p.partial + ((size_t)n * nblk + blk) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = v[i];
+        __threadfence();
+        const unsigned prev = atomicAdd(&p.counters[n], 1u);
+        sm.flag = (prev == (unsigned)(nblk - 1));
+    }
+    __syncthreads();
+    if (!sm.flag) return;
+    __threadfence();
+    double t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = 0.0;
+    for (int k = threadIdx.x; k < nblk; k += kNT) {
+        const double* srcp = p.partial + ((size_t)n * nblk + k) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] += __ldcg(srcp + i);
+    }
+    block_sum<8, kNT>(t, sm.red);
+    if (threadIdx.x == 0) {
+        double* sums = p.sums + (size_t)n * p.sums_stride;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sums[i] = t[i];
+        p.counters[n] = 0u;
+        if (p.finalize == FIN_LOSS) {
+            const double inv = 1.0 / ((double)p.Hout * (double)p.Wout);
+            double* so = p.out + MMIF_LOSS_HEAD + (size_t)n * MMIF_LOSS_PER_SAMPLE;
+            so[0] = t[0] * inv; so[1] = t[2] * inv; so[2] = t[4] * inv;   // ssim1, cs1, sigma1
+            so[3] = t[1] * inv; so[4] = t[3] * inv; so[5] = t[5] * inv;   // ssim2, cs2, sigma2
+            __threadfence();
+            const unsigned prev = atomicAdd(&p.counters[p.B], 1u);
+            if (prev == (unsigned)(p.B - 1)) {
+                __threadfence();
+                double a1 = 0.0, a2 = 0.0, px = 0.0, gr = 0.0;
+                for (int k = 0; k < p.B; ++k) {
+                    const double* q = p.sums + (size_t)k * p.sums_stride;
+                    a1 += __ldcg(q + 0) * inv; a2 += __ldcg(q + 1) * inv; px += __ldcg(q + 6); gr += __ldcg(q + 7);
+                }
+                const double npx = (double)p.B * (double)p.H * (double)p.W;
+                const double l_ssim = (double)p.w_ssim * (1.0 - 0.5 * (a1 / p.B + a2 / p.B));
+                const double l_pix = (double)p.w_pixel * px / npx;
+                const double l_grad = (double)p.w_grad * gr / npx;
+                p.out[MMIF_LOSS_SSIM] = l_ssim;
+                p.out[MMIF_LOSS_PIXEL] = l_pix;
+                p.out[MMIF_LOSS_GRAD] = l_grad;
+                p.out[MMIF_LOSS_TOTAL] = l_ssim + l_pix + l_grad;
+                p.counters[p.B] = 0u;
+            }
+        }
+    }
+}
+
+// ---- host-side geometry + launcher (defined in moment_fwd.cu) ----------------------------------
+struct FwdLaunch {
+    int win;                 // 3, 5, 9, 11 or 17
+    double sigma;
+    int epi;                 // EPI_*
+    int finalize;            // FIN_*
+    int do_sobel;
+    float data_range;
+    MmifLossCfg cfg;         // combine / norm / weights (EPI_SSIM + do_sobel)
+};
+int fwd_seg_rows(int rows, int other_ctas);
+size_t fwd_ws_bytes(int win, int B, int H, int W);       // counters + partials (sums live elsewhere)
+// ws: zero-initialised workspace of fwd_ws_bytes; sums: B x sums_stride doubles (device).
+int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, const float* y, int B, int H, int W,
+                      double* sums, long long sums_stride, double* out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace mmif

@@ -1,0 +1,34 @@
+"""Parity gates of SURVEY.md §8(c), shared by the GPU tests."""
+import numpy as np
+
+RTOL = 1e-5      # north_star: floating-point results within 1e-5 relative in fp32
+ATOL = 1e-7      # absolute floor for scalars that are ~0 (cc, scd, nabf on random data)
+
+
+def scalar_ok(new, ref32, ref64):
+    """|new-ref32| <= RTOL|ref32| (+ATOL)  OR  new at least as close to the fp64 truth as the fp32
+    reference is (the reference's own fp32 noise reaches ~8e-6 on real images)."""
+    new, ref32, ref64 = float(new), float(ref32), float(ref64)
+    if not np.isfinite(new):
+        return np.isnan(new) and np.isnan(ref32)
+    if abs(new - ref32) <= RTOL * abs(ref32) + ATOL:
+        return True
+    return abs(new - ref64) <= abs(ref32 - ref64)
+
+
+def assert_scalar(name, new, ref32, ref64):
+    assert scalar_ok(new, ref32, ref64), (
+        f'{name}: new={float(new)!r} ref32={float(ref32)!r} ref64={float(ref64)!r} '
+        f'rel32={abs(float(new) - float(ref32)) / max(abs(float(ref32)), 1e-300):.3e} '
+        f'rel64={abs(float(new) - float(ref64)) / max(abs(float(ref64)), 1e-300):.3e}')
+
+
+def grad_report(new, ref64, rtol=RTOL):
+    """max-norm gate against the fp64 oracle; returns (ok_fraction_bad, max_rel, where)."""
+    new = np.asarray(new, dtype=np.float64)
+    ref64 = np.asarray(ref64, dtype=np.float64)
+    scale = np.abs(ref64).max()
+    diff = np.abs(new - ref64)
+    bad = diff > rtol * scale
+    where = np.unravel_index(np.argmax(diff), diff.shape)
+    return bad.mean(), (diff.max() / scale if scale > 0 else diff.max()), where

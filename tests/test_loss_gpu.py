@@ -1,0 +1,160 @@
+"""GPU parity of the fused fusion objective (forward + backward) against the oracle and the
+golden vectors of the real reference.  Everything goes through the drop-in modules, i.e. through
+the C ABI of libmmif_b200.so."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gates
+from oracle import fusion_loss as OL
+
+pytestmark = pytest.mark.gpu
+LG = np.load(cases.HERE + '/loss_golden.npz')
+
+
+def _mods():
+    import mmif_b200  # noqa: F401
+    from mmif_b200.core import loss as ML
+    return ML
+
+
+def T(x, dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dt)
+
+
+def run_new(a, b, f, need_grad=True, pixel=('l1', 'max'), grad=('l1', 'max'), w=(1.0, 0.01, 0.1)):
+    ML = _mods()
+    A, B_, F_ = a.cuda(), b.cuda(), f.cuda().requires_grad_(need_grad)
+    l1 = ML.SSIMLoss('ssim', weight=w[0])(A, B_, F_)
+    l2 = ML.PixelLoss(pixel[0], weight=w[1])(A, B_, F_, mode=pixel[1])
+    l3 = ML.GradLoss(grad[0], weight=w[2])(A, B_, F_, mode=grad[1])
+    grads = None
+    if need_grad:
+        grads = [torch.autograd.grad(t, F_, retain_graph=True)[0].cpu().numpy() for t in (l1, l2, l3)]
+    return [l1.item(), l2.item(), l3.item()], grads
+
+
+@pytest.mark.parametrize('name', cases.LOSS_CASES)
+def test_loss_forward_vs_golden(name):
+    a, b, f = (T(x) for x in cases.loss_case(name))
+    vals, _ = run_new(a, b, f, need_grad=False)
+    for k, nm in enumerate(('ssim', 'pixel', 'grad')):
+        gates.assert_scalar(f'{name}/{nm}', vals[k], LG[f'{name}/f32/loss'][k], LG[f'{name}/f64/loss'][k])
+
+
+@pytest.mark.parametrize('name', cases.LOSS_CASES)
+def test_ssim_module_dict_vs_golden(name):
+    ML = _mods()
+    a, b, f = (T(x).cuda() for x in cases.loss_case(name))
+    mod = ML.SSIM(11, 1.0).cuda()
+    d1, d2 = mod(a, f), mod(b, f)
+    got = np.stack([d1['ssim'].cpu().numpy(), d1['cs'].cpu().numpy(), d1['sigma'].cpu().numpy(),
+                    d2['ssim'].cpu().numpy(), d2['cs'].cpu().numpy(), d2['sigma'].cpu().numpy()])
+    r32, r64 = LG[f'{name}/f32/ssim_dict'], LG[f'{name}/f64/ssim_dict']
+    for i in range(got.shape[0]):
+        for j in range(got.shape[1]):
+            gates.assert_scalar(f'{name}/dict[{i},{j}]', got[i, j], r32[i, j], r64[i, j])
+
+
+@pytest.mark.parametrize('name', cases.LOSS_CASES)
+def test_loss_backward_vs_fp64_oracle(name):
+    """Gradient gate of SURVEY.md 8(c): max-norm error against the fp64 oracle <= 1e-5 max|g|, or —
+    where the fp32 reference itself is noisier than that (flat regions: 1/C2 amplifies the rounding
+    of the moments) — no worse than the reference's own fp32 error on the same input."""
+    a, b, f = (T(x) for x in cases.loss_case(name))
+    _, grads = run_new(a, b, f, need_grad=True)
+    ref = LG[f'{name}/f64/grad']
+    tot64 = ref.sum(axis=0)
+    ref32_err = np.abs(LG[f'{name}/f32/grad_total'] - tot64).max() / np.abs(tot64).max()
+    frac, mx, where = gates.grad_report(grads[0], ref[0])
+    scale_ratio = np.abs(ref[0]).max() / np.abs(tot64).max()
+    assert mx <= max(gates.RTOL, ref32_err / max(scale_ratio, 1e-30)), \
+        f'{name}: ssim grad max-norm err {mx:.3e} at {where} (fp32 reference: {ref32_err:.3e})'
+    for k, nm in ((1, 'pixel'), (2, 'grad')):
+        frac, mx, where = gates.grad_report(grads[k], ref[k])
+        if name in cases.LOSS_GRAD_TIE_CASES:
+            continue   # exact ties: sign(0) of a value that is exactly / nearly 0
+        assert frac <= 1e-4, f'{name}: {nm} grad: {frac:.2e} of elements differ, max {mx:.3e} at {where}'
+
+
+def test_total_backward_and_memo_single_node():
+    """train.py:64-71: total = l1+l2+l3; one backward; gradient = sum of the three terms."""
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    A, B_, F_ = a.cuda(), b.cuda(), f.cuda().requires_grad_(True)
+    tot = ML.SSIMLoss('ssim', weight=1.0)(A, B_, F_) + ML.PixelLoss('l1', 0.01)(A, B_, F_, mode='max') \
+        + ML.GradLoss('l1', 0.1)(A, B_, F_, mode='max')
+    tot.backward()
+    ref = LG['rand_3x64x96/f64/grad'].sum(axis=0)
+    frac, mx, where = gates.grad_report(F_.grad.cpu().numpy(), ref)
+    assert frac <= 1e-4, (frac, mx, where)
+    gates.assert_scalar('total', tot.item(), LG['rand_3x64x96/f32/loss'].sum(), LG['rand_3x64x96/f64/loss'].sum())
+
+
+@pytest.mark.parametrize('pixel', [('l1', 'avg'), ('l2', 'max'), ('l2', 'avg')])
+def test_secondary_modes(pixel):
+    a, b, f = (T(x) for x in cases.loss_case('rand_2x40x37'))
+    vals, grads = run_new(a, b, f, True, pixel=pixel, grad=pixel)
+    for dt, store in ((torch.float32, 'r32'), (torch.float64, 'r64')):
+        pass
+    r32 = [OL.pixel_loss(a, b, f, pixel[0], 0.01, pixel[1]).item(), OL.grad_loss(a, b, f, pixel[0], 0.1, pixel[1]).item()]
+    ad, bd = a.double(), b.double()
+    fd = f.double().requires_grad_(True)
+    p64 = OL.pixel_loss(ad, bd, fd, pixel[0], 0.01, pixel[1])
+    g64 = OL.grad_loss(ad, bd, fd, pixel[0], 0.1, pixel[1])
+    gp, = torch.autograd.grad(p64, fd)
+    gg, = torch.autograd.grad(g64, fd)
+    gates.assert_scalar('pixel', vals[1], r32[0], p64.item())
+    gates.assert_scalar('grad', vals[2], r32[1], g64.item())
+    for got, ref, nm in ((grads[1], gp.numpy(), 'pixel'), (grads[2], gg.numpy(), 'grad')):
+        frac, mx, where = gates.grad_report(got, ref)
+        assert frac <= 1e-3, f'{nm} {pixel}: {frac:.2e} differ, max {mx:.3e} at {where}'
+
+
+def test_errors_match_reference():
+    ML = _mods()
+    x = torch.rand(1, 1, 32, 32, device='cuda')
+    with pytest.raises(ValueError):
+        ML.SSIMLoss('nope')(x, x, x)
+    with pytest.raises(ValueError):
+        ML.PixelLoss('l3')(x, x, x, mode='max')
+    assert ML.PixelLoss('l1')(x, x, x, mode='other') is None
+    with pytest.raises(NotImplementedError):
+        ML.SSIMLoss('ms-ssim')(x, x, x)
+    with pytest.raises(Exception):
+        ML.SSIMLoss('ssim')(x.cpu(), x.cpu(), x.cpu())   # no CPU fallback
+
+
+@pytest.mark.parametrize('shape', [(1, 1024, 1224), (2, 517, 1030), (1, 300, 2050)])
+def test_loss_config_sizes_vs_live_oracle(shape):
+    """BASELINE config 1 shape (1224x1024) and ragged multi-strip / multi-segment shapes."""
+    g = torch.Generator().manual_seed(sum(shape))
+    a, b, f = (torch.rand((shape[0], 1) + shape[1:], generator=g) for _ in range(3))
+    vals, grads = run_new(a, b, f, True)
+    r32 = [t.item() for t in OL.train_objective(a, b, f)]
+    (l64, g64) = OL.train_objective_grad(a.double(), b.double(), f.double())
+    for k, nm in enumerate(('ssim', 'pixel', 'grad')):
+        gates.assert_scalar(f'{shape}/{nm}', vals[k], r32[k], l64[k].item())
+    tot = grads[0] + grads[1] + grads[2]
+    frac, mx, where = gates.grad_report(tot, g64.numpy())
+    assert frac <= 1e-4, f'{shape}: total grad {frac:.2e} differ, max {mx:.3e} at {where}'
+
+
+def test_backward_is_linear_in_upstream_and_deterministic():
+    """Size-independent properties at a large size (no oracle needed)."""
+    ML = _mods()
+    g = torch.Generator().manual_seed(5)
+    a, b, f = (torch.rand(2, 1, 1536, 2048, generator=g).cuda() for _ in range(3))
+    f.requires_grad_(True)
+    l1 = ML.SSIMLoss('ssim')(a, b, f)
+    l2 = ML.PixelLoss('l1', 0.01)(a, b, f, mode='max')
+    l3 = ML.GradLoss('l1', 0.1)(a, b, f, mode='max')
+    parts = [torch.autograd.grad(t, f, retain_graph=True)[0] for t in (l1, l2, l3)]
+    tot, = torch.autograd.grad(2.0 * l1 + 3.0 * l2 - 0.5 * l3, f, retain_graph=True)
+    ref = 2.0 * parts[0] + 3.0 * parts[1] - 0.5 * parts[2]
+    assert (tot - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    tot2, = torch.autograd.grad(2.0 * l1 + 3.0 * l2 - 0.5 * l3, f, retain_graph=True)
+    assert torch.equal(tot, tot2)
+    v1 = ML.SSIMLoss('ssim')(a, b, f.detach().clone()).item()
+    assert v1 == l1.item()
