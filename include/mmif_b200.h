@@ -14,8 +14,10 @@
  *   - return 0 on success, negative MMIF_E_* on error; mmif_last_error() gives the text for the
  *     calling thread; no exception, abort or device synchronisation crosses the ABI;
  *   - the caller owns every buffer, including the workspace `ws` (size from the matching
- *     *_workspace_bytes call; must be zero-filled once before first use — the kernels leave it
- *     zeroed again); the library never allocates or frees device memory;
+ *     *_workspace_bytes call; 256-byte aligned; must be zero-filled once before its first use
+ *     WITH A GIVEN SHAPE — the kernels leave their counters zeroed again, but the carve-up
+ *     depends on the shape, so re-zero it (or use another buffer) when the shape changes; one
+ *     workspace serves one stream at a time); the library never allocates or frees device memory;
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and results stay on the
  *     device; re-entrant (no mutable globals besides __constant__ tap tables written per launch
  *     configuration under a mutex).

@@ -101,16 +101,20 @@ def ensure_device(device):
 
 
 _ws_cache = {}
+_WS_CACHE_CAP = 16
 
 
-def workspace(device, nbytes, tag):
-    """Zero-initialised, cached per (device, stream, tag); grows monotonically.  The kernels
-    leave their counters zeroed, so the buffer is only cleared when (re)allocated."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
-    buf = _ws_cache.get(key)
+def workspace(device, nbytes, tag, shape=None):
+    """Zero-initialised workspace, cached per (device, stream, tag, shape).  The kernels leave their
+    counters zeroed, but the carve-up of a workspace depends on the problem shape, so a buffer is
+    only ever reused for the shape it was first zeroed for (small LRU)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag, shape)
+    buf = _ws_cache.pop(key, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
+    _ws_cache[key] = buf            # re-insert: most recently used last
+    while len(_ws_cache) > _WS_CACHE_CAP:
+        _ws_cache.pop(next(iter(_ws_cache)))
     return buf
 
 

@@ -50,7 +50,7 @@ class _FusedObjective(torch.autograd.Function):
         nws = lib.mmif_loss_workspace_bytes(B, H, W)
         if nws == 0:
             raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11')
-        ws = L.workspace(dev, nws, 'loss')
+        ws = L.workspace(dev, nws, 'loss', (B, H, W))
         with torch.cuda.device(dev):
             L.check(lib.mmif_fusion_loss_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),
                                              out.data_ptr(), None, ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
@@ -71,7 +71,7 @@ class _FusedObjective(torch.autograd.Function):
         g = torch.stack([zero if t is None else t.to(torch.float32).reshape(()) for t in (g_ssim, g_pix, g_grad)])
         dF = torch.empty_like(y)
         cfg = _cfg(*ctx.cfg_key)
-        ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss')
+        ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
         with torch.cuda.device(dev):
             L.check(lib.mmif_fusion_loss_bwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),
                                              g.data_ptr(), dF.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
@@ -275,7 +275,7 @@ class TVLoss(nn.Module):
         dev = x.device
         L.ensure_device(dev)
         out = torch.empty(1, dtype=torch.float64, device=dev)
-        ws = L.workspace(dev, lib.mmif_metric_workspace_bytes(xc.shape[0], h, w), 'metric')
+        ws = L.workspace(dev, lib.mmif_metric_workspace_bytes(xc.shape[0], h, w), 'metric', (xc.shape[0], h, w))
         with torch.cuda.device(dev):
             L.check(lib.mmif_tv_loss(xc.data_ptr(), xc.shape[0], h, w, L.NORM[self.mode], float(self.weight),
                                      out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))

@@ -1,0 +1,322 @@
+"""Drop-in mirror of the reference ``core/metric.py`` call surface on the B200 kernels.
+
+Same 17 function names, argument meaning and return types as the reference
+(metric.py:16-21): every function returns a 0-dim tensor (``calc_mul_info`` in float64, the rest
+float32) on the device of its inputs.  ``eval.py`` hands CPU tensors to these functions
+(eval.py:198-200 discards the ``.to(device)`` results); they are uploaded once per image (cached
+by tensor identity) and ALL arithmetic runs on the GPU — there is no CPU compute path.
+
+``eval_metrics_batch`` is the batched entry (N pairs per launch) the sharded evaluation and the
+benchmark use; the per-function drop-ins share kernel results through a small per-pair memo so
+the 20-odd calls of ``eval_metrics`` (eval.py:29-75) cost one launch per kernel family.
+"""
+import ctypes
+import weakref
+
+import torch
+
+from .. import _lib as L
+
+__all__ = [
+    'calc_mean', 'calc_std', 'calc_ag', 'calc_sf', 'calc_mse', 'calc_psnr',
+    'calc_cc', 'calc_scd', 'calc_entropy', 'calc_cross_ent', 'calc_mul_info',
+    'calc_Qabf', 'calc_Nabf', 'calc_Labf', 'calc_ssim', 'calc_msssim',
+    'calc_viff'
+]
+
+METRIC_NAMES = ('sd', 'ag', 'sf', 'mse', 'psnr', 'cc', 'scd', 'en', 'ce', 'mi',
+                'qabf', 'nabf', 'labf', 'ssim', 'msssim', 'viff')   # eval.py:52-68
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise L.MmifError('no CUDA device: the metric suite has no CPU compute path')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class _UploadCache:
+    """CPU tensor -> device copy, keyed on identity + version (eval.py passes the same three CPU
+    tensors to ~20 metric calls)."""
+
+    def __init__(self, cap=8):
+        self.cap, self.items = cap, []
+
+    def get(self, t):
+        if t.is_cuda:
+            return t
+        for ref, ver, dev in self.items:
+            if ref() is t and ver == t._version:
+                return dev
+        dev = t.to(_default_device(), non_blocking=False)
+        self.items.append((weakref.ref(t), t._version, dev))
+        if len(self.items) > self.cap:
+            self.items.pop(0)
+        return dev
+
+
+_uploads = _UploadCache()
+
+
+def _prep(*imgs):
+    """-> list of contiguous float32 (N,H,W) device views + (N,H,W) + the device results go back to."""
+    home = imgs[0].device
+    out, shape = [], None
+    for i, t in enumerate(imgs):
+        d = _uploads.get(t)
+        d, n, h, w = L.as_f32_3d(d, f'img{i}')
+        if shape is None:
+            shape = (n, h, w)
+        elif shape != (n, h, w):
+            raise L.MmifError(f'shape mismatch: {shape} vs {(n, h, w)}')
+        out.append(d)
+    L.ensure_device(out[0].device)
+    return out, shape, home
+
+
+class _PairMemo:
+    """Results of one kernel family for one (a, b, f) triple, keyed on storage identity/version."""
+
+    def __init__(self, cap=12):
+        self.cap, self.items = cap, []
+
+    @staticmethod
+    def _key(kind, tensors, extra):
+        return (kind, extra) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+
+    def get(self, kind, tensors, extra, compute):
+        key = self._key(kind, tensors, extra)
+        for k, refs, val in self.items:
+            if k == key and all(r() is t for r, t in zip(refs, tensors)):
+                return val
+        val = compute()
+        self.items.append((key, tuple(weakref.ref(t) for t in tensors), val))
+        if len(self.items) > self.cap:
+            self.items.pop(0)
+        return val
+
+
+_memo = _PairMemo()
+
+
+def _ws(dev, n, h, w):
+    lib = L.load()
+    nbytes = lib.mmif_metric_workspace_bytes(n, h, w)
+    if nbytes == 0:
+        raise L.MmifError(f'unsupported shape {(n, h, w)}')
+    return L.workspace(dev, nbytes, 'metric', (n, h, w))
+
+
+def _call(fn_name, imgs, shape, out_doubles, *extra_args):
+    lib = L.load()
+    n, h, w = shape
+    dev = imgs[0].device
+    out = torch.empty(n * out_doubles, dtype=torch.float64, device=dev)
+    ws = _ws(dev, n, h, w)
+    with torch.cuda.device(dev):
+        L.check(getattr(lib, fn_name)(imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, *extra_args,
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+    return out.view(n, out_doubles)
+
+
+def _stats(a, b, f):
+    def run():
+        imgs, shape, _ = _prep(a, b, f)
+        return _call('mmif_stats', imgs, shape, L.ST_COUNT)
+    return _memo.get('stats', (a, b, f), None, run)
+
+
+def _hist(a, b, f, want_counts=False):
+    def run():
+        lib = L.load()
+        imgs, (n, h, w), _ = _prep(a, b, f)
+        dev = imgs[0].device
+        counts = torch.empty(n * L.HIST_WORDS, dtype=torch.int32, device=dev)
+        ent = torch.empty(n * L.EN_COUNT, dtype=torch.float64, device=dev)
+        ws = _ws(dev, n, h, w)
+        with torch.cuda.device(dev):
+            L.check(lib.mmif_hist(imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, counts.data_ptr(),
+                                  ent.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+        return counts.view(n, L.HIST_WORDS), ent.view(n, L.EN_COUNT)
+    return _memo.get('hist', (a, b, f), None, run)
+
+
+def _qabf(a, b, f, Lexp):
+    def run():
+        imgs, shape, _ = _prep(a, b, f)
+        return _call('mmif_qabf', imgs, shape, 4, ctypes.c_float(Lexp))
+    return _memo.get('qabf', (a, b, f), float(Lexp), run)
+
+
+def _ssim2(a, b, f, win_size, data_range, use_padding):
+    if use_padding:
+        raise NotImplementedError('use_padding=True is not built yet')
+    def run():
+        imgs, shape, _ = _prep(a, b, f)
+        return _call('mmif_ssim', imgs, shape, 4, int(win_size), ctypes.c_float(data_range), 0)
+    return _memo.get('ssim', (a, b, f), (int(win_size), float(data_range)), run)
+
+
+def _msssim2(a, b, f, win_size, data_range, use_padding):
+    if use_padding:
+        raise NotImplementedError('use_padding=True is not built yet')
+    def run():
+        imgs, shape, _ = _prep(a, b, f)
+        return _call('mmif_msssim', imgs, shape, L.MSSSIM_DOUBLES, int(win_size), ctypes.c_float(data_range))
+    return _memo.get('msssim', (a, b, f), (int(win_size), float(data_range)), run)
+
+
+def _viff3(a, b, f):
+    def run():
+        imgs, shape, _ = _prep(a, b, f)
+        return _call('mmif_viff', imgs, shape, L.VIFF_DOUBLES)
+    return _memo.get('viff', (a, b, f), None, run)
+
+
+def _scalar(row_value, home, dtype=torch.float32):
+    """0-dim tensor on the caller's device (the global mean over all pairs in the batch is what
+    the reference computes for N>1; these drop-ins are called with N == 1 by every script)."""
+    v = row_value.to(dtype)
+    return v.to(home) if v.device != home else v
+
+
+def _single(t, what):
+    if t.dim() == 4 and t.shape[0] != 1:
+        raise NotImplementedError(f'{what}: the drop-in functions take one image pair (N=1) like every reference caller; '
+                                  'use eval_metrics_batch for batches')
+
+
+# 1. mean
+def calc_mean(img):
+    _single(img, 'calc_mean')
+    return _scalar(_stats(img, img, img)[0, 0], img.device)
+
+
+# 2. sd
+def calc_std(img):
+    _single(img, 'calc_std')
+    return _scalar(_stats(img, img, img)[0, 1], img.device)
+
+
+# 3. ag
+def calc_ag(img):
+    _single(img, 'calc_ag')
+    return _scalar(_stats(img, img, img)[0, 2], img.device)
+
+
+# 4. sf
+def calc_sf(img):
+    _single(img, 'calc_sf')
+    return _scalar(_stats(img, img, img)[0, 3], img.device)
+
+
+# 5. mse  (kernel slot: a vs f)
+def calc_mse(img1, img2):
+    _single(img1, 'calc_mse')
+    return _scalar(_stats(img1, img1, img2)[0, 4], img1.device)
+
+
+# 6. psnr — pure scalar arithmetic on the mse tensor, as in the reference (metric.py:72-76)
+def calc_psnr(mse, L=1.0, root=False):
+    if root:
+        return 20.0 * torch.log10(L / mse**0.5)
+    return 10.0 * torch.log10(L**2 / mse)
+
+
+# 7. cc
+def calc_cc(img1, img2):
+    _single(img1, 'calc_cc')
+    return _scalar(_stats(img1, img1, img2)[0, 6], img1.device)
+
+
+# 8. scd
+def calc_scd(img1, img2, imgf):
+    _single(img1, 'calc_scd')
+    return _scalar(_stats(img1, img2, imgf)[0, 8], img1.device)
+
+
+# 9. en
+def calc_entropy(img):
+    _single(img, 'calc_entropy')
+    return _scalar(_hist(img, img, img)[1][0, 2], img.device)
+
+
+# 11. ce
+def calc_cross_ent(img1, img2):
+    _single(img1, 'calc_cross_ent')
+    return _scalar(_hist(img1, img1, img2)[1][0, 5], img1.device)
+
+
+# 12. mi — float64 like the reference (metric.py:179-188)
+def calc_mul_info(img1, img2, normalized=False):
+    _single(img1, 'calc_mul_info')
+    ent = _hist(img1, img1, img2)[1]
+    return _scalar(ent[0, 9] if normalized else ent[0, 7], img1.device, torch.float64)
+
+
+# 13. Qabf
+def calc_Qabf(img1, img2, imgf, L=1.5, full=False):
+    _single(img1, 'calc_Qabf')
+    q = _qabf(img1, img2, imgf, L)
+    if full:
+        return tuple(_scalar(q[0, i], img1.device) for i in range(3))
+    return _scalar(q[0, 0], img1.device)
+
+
+# 14. Nabf
+def calc_Nabf(img1, img2, imgf, L=1.5, modified=True):
+    _single(img1, 'calc_Nabf')
+    return _scalar(_qabf(img1, img2, imgf, L)[0, 1 if modified else 3], img1.device)
+
+
+# 15. Labf
+def calc_Labf(img1, img2, imgf, L=1.5):
+    _single(img1, 'calc_Labf')
+    return _scalar(_qabf(img1, img2, imgf, L)[0, 2], img1.device)
+
+
+# 16. ssim
+def calc_ssim(img1, img2, win_size=11, data_range=255.0, use_padding=False, size_average=True, full=False):
+    _single(img1, 'calc_ssim')
+    if not size_average:
+        raise NotImplementedError('size_average=False (SSIM maps) is not built yet')
+    r = _ssim2(img1, img1, img2, win_size, data_range, use_padding)
+    if full:
+        return _scalar(r[0, 0], img1.device), _scalar(r[0, 1], img1.device)
+    return _scalar(r[0, 0], img1.device)
+
+
+# 17. msssim
+def calc_msssim(img1, img2, win_size=11, data_range=255.0, use_padding=False):
+    _single(img1, 'calc_msssim')
+    return _scalar(_msssim2(img1, img1, img2, win_size, data_range, use_padding)[0, 0], img1.device)
+
+
+# 18. viff
+def calc_viff(img1, img2, imgf, simple=True):
+    _single(img1, 'calc_viff')
+    return _scalar(_viff3(img1, img2, imgf)[0, 1 if simple else 0], img1.device)
+
+
+# ---- batched entries (not in the reference; used by the sharded evaluation and the benchmark) ----
+def eval_metrics_batch(img1, img2, imgf):
+    """(N,1,H,W) x3 on the GPU -> (N,16) float64 tensor, columns in eval.py:52-68 order."""
+    for t in (img1, img2, imgf):
+        L.require_cuda(t, 'image')
+    imgs, shape, _ = _prep(img1, img2, imgf)
+    return _call('mmif_eval_suite', imgs, shape, L.EVAL_METRICS)
+
+
+def eval_metrics(img1, img2, imgf):
+    """The dict eval.py:29-75 builds for one pair (python floats), through the fused suite entry."""
+    _single(img1, 'eval_metrics')
+    imgs, shape, _ = _prep(img1, img2, imgf)
+    row = _call('mmif_eval_suite', imgs, shape, L.EVAL_METRICS)[0].tolist()
+    return dict(zip(METRIC_NAMES, row))
+
+
+def histograms(img1, img2, imgf):
+    """Integer counts (hist_a, hist_b, hist_f, joint_af, joint_bf) of one pair, as int64 CPU tensors."""
+    _single(img1, 'histograms')
+    c = _hist(img1, img2, imgf)[0][0].to(torch.int64).cpu()
+    return (c[0:256], c[256:512], c[512:768], c[768:768 + 65536].view(256, 256),
+            c[768 + 65536:].view(256, 256))

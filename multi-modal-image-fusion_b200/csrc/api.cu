@@ -60,8 +60,11 @@ void make_taps(Taps* t, int win, double sigma) {
     double s2 = 0.0;   // sum of the reference's float32 2-D outer-product window (loss.py:36-37)
     for (int i = 0; i < win; ++i)
         for (int j = 0; j < win; ++j) s2 += (double)(float)(t->w[i] * t->w[j]);
+    double s1 = 0.0;
+    for (int i = 0; i < win; ++i) s1 += (double)t->w[i];
     t->wsum = (float)s2;
     t->weps = (float)(s2 - 1.0);
+    t->wrho = (float)(s2 / (s1 * s1) - 1.0);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

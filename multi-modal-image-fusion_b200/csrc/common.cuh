@@ -34,6 +34,9 @@ struct Taps {          // Gaussian taps of one window, passed by value in kernel
     float w[kMaxWin];  // float32 taps exactly as the reference builds them (loss.py:24-30)
     float wsum;        // sum of the reference's float32 2-D outer-product window (double -> float)
     float weps;        // wsum - 1 (computed in double)
+    float wrho;        // wsum / (sum w)^2 - 1: the separable taps w_i*w_j (exact products) do not sum to
+                       // what the reference's rounded products fl(w_i*w_j) sum to; ~1e-8, matters only where
+                       // the variance of a flat region is compared with C2 ~ 1e-3
 };
 void make_taps(Taps* t, int win, double sigma);
 

@@ -78,7 +78,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         mbar_fence_init();
     }
     __syncthreads();
-    const Shift sh = tile_shift(src.img[0], src.img[1], src.img[2], p.H, p.W, i0 + p.seg_rows / 2, j0 + kTG / 2, p.taps);
+    const Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, R0, iend - R0 + HALO, jw0, p.taps);
     const float g_ssim = __ldg(p.gout + 0), g_pix = __ldg(p.gout + 1), g_grad = __ldg(p.gout + 2);
     const float npx = (float)p.B * (float)p.H * (float)p.W;
     const float k_ssim = g_ssim * p.w_ssim * (-0.5f) / ((float)p.B * (float)p.Hout * (float)p.Wout);

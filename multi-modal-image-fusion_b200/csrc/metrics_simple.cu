@@ -1,0 +1,337 @@
+// Per-pixel metric families of reference core/metric.py: first/second-order statistics
+// (SD/AG/SF/MSE/CC/SCD), histograms + entropies (EN/CE/MI), edge preservation (Qabf/Nabf/Labf),
+// and TVLoss of core/loss.py.  Every kernel reads its inputs once, accumulates in registers,
+// reduces per block with warp shuffles in double, and the last block of a pair finishes that pair
+// in a fixed order (deterministic, no float atomics).
+#include "metrics.cuh"
+
+namespace mmif {
+
+// =============================================================================== statistics
+// sums: 0 Sa 1 Sb 2 Sf 3 Saa 4 Sbb 5 Sff 6 Sab 7 Saf 8 Sbf 9 Sag 10 Sdx2 11 Sdy2 12 S(a-f)^2 13 S(b-f)^2
+constexpr int kStatK = 14;
+
+__global__ void __launch_bounds__(256)
+stats_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ F, int H, int W, int rpb,
+             double* partial, unsigned* counters, double* out, long long ostride) {
+    __shared__ double red[kStatK * 8];
+    __shared__ int flag;
+    const int n = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+    const size_t off = (size_t)n * H * W;
+    const float* a = A + off; const float* b = Bm + off; const float* f = F + off;
+    const int r0 = blk * rpb, r1 = min(r0 + rpb, H);
+    double acc[kStatK];
+#pragma unroll
+    for (int i = 0; i < kStatK; ++i) acc[i] = 0.0;
+    for (int c = threadIdx.x; c < W; c += 256) {
+        float s[kStatK];
+#pragma unroll
+        for (int i = 0; i < kStatK; ++i) s[i] = 0.f;
+        float ff = __ldg(f + (size_t)r0 * W + c);
+        for (int r = r0; r < r1; ++r) {
+            const size_t p = (size_t)r * W + c;
+            const float fa = __ldg(a + p), fb = __ldg(b + p);
+            const bool hasx = (c + 1 < W), hasy = (r + 1 < H);
+            const float fr = hasx ? __ldg(f + p + 1) : ff;
+            const float fd = hasy ? __ldg(f + p + W) : ff;
+            s[0] += fa; s[1] += fb; s[2] += ff;
+            s[3] = fmaf(fa, fa, s[3]); s[4] = fmaf(fb, fb, s[4]); s[5] = fmaf(ff, ff, s[5]);
+            s[6] = fmaf(fa, fb, s[6]); s[7] = fmaf(fa, ff, s[7]); s[8] = fmaf(fb, ff, s[8]);
+            const float dx = fr - ff, dy = fd - ff;
+            if (hasx) s[10] = fmaf(dx, dx, s[10]);
+            if (hasy) s[11] = fmaf(dy, dy, s[11]);
+            if (hasx && hasy) s[9] += sqrtf((dx * dx + dy * dy) * 0.5f);     // metric.py:44
+            const float ea = fa - ff, eb = fb - ff;
+            s[12] = fmaf(ea, ea, s[12]); s[13] = fmaf(eb, eb, s[13]);
+            ff = fd;
+        }
+#pragma unroll
+        for (int i = 0; i < kStatK; ++i) acc[i] += (double)s[i];
+    }
+    double t[kStatK];
+    if (!block_finish<kStatK, 256>(acc, red, &flag, partial, counters, n, blk, nblk, t)) return;
+    // ---- last block, thread 0: the metrics of this pair (double arithmetic on the raw sums) ----
+    const double P = (double)H * (double)W;
+    const double ma = t[0] / P, mb = t[1] / P, mf = t[2] / P;
+    const double vaa = t[3] - t[0] * t[0] / P, vbb = t[4] - t[1] * t[1] / P, vff = t[5] - t[2] * t[2] / P;   // P * variance
+    const double cab = t[6] - t[0] * t[1] / P, caf = t[7] - t[0] * t[2] / P, cbf = t[8] - t[1] * t[2] / P;   // P * covariance
+    double* o = out + (size_t)n * ostride;
+    o[MMIF_ST_MEAN_F] = mf;
+    o[MMIF_ST_SD] = sqrt(fmax(vff, 0.0) / P);
+    o[MMIF_ST_AG] = t[9] / ((double)(H - 1) * (double)(W - 1));
+    o[MMIF_ST_SF] = sqrt(t[11] / ((double)(H - 1) * (double)W) + t[10] / ((double)H * (double)(W - 1)));
+    o[MMIF_ST_MSE_AF] = t[12] / (255.0 * 255.0) / P;                       // metric.py:63-68
+    o[MMIF_ST_MSE_BF] = t[13] / (255.0 * 255.0) / P;
+    o[MMIF_ST_CC_AF] = caf / sqrt(vaa * vff);                              // metric.py:80-91
+    o[MMIF_ST_CC_BF] = cbf / sqrt(vbb * vff);
+    // scd = cc(f-a, b) + cc(f-b, a) (metric.py:95-99) from second moments
+    const double v_fa = vff + vaa - 2.0 * caf, v_fb = vff + vbb - 2.0 * cbf;
+    o[MMIF_ST_SCD] = (cbf - cab) / sqrt(v_fa * vbb) + (caf - cab) / sqrt(v_fb * vaa);
+    o[MMIF_ST_MEAN_A] = ma; o[MMIF_ST_MEAN_B] = mb;
+    o[MMIF_ST_SD_A] = sqrt(fmax(vaa, 0.0) / P); o[MMIF_ST_SD_B] = sqrt(fmax(vbb, 0.0) / P);
+    o[MMIF_ST_CC_AB] = cab / sqrt(vaa * vbb);
+    o[14] = 0.0; o[15] = 0.0;
+}
+
+int stats_rows_per_block(int N, int H) {
+    int rpb = (int)(((long long)N * H + 591) / 592);
+    return rpb < 1 ? 1 : (rpb > 32 ? 32 : rpb);
+}
+
+int launch_stats(const float* a, const float* b, const float* f, int N, int H, int W, double* out, long long ostride, MetricWs& ws,
+                 cudaStream_t st) {
+    if (H < 2 || W < 2) { set_error("stats: H and W must be >= 2"); return MMIF_E_SHAPE; }
+    const int rpb = stats_rows_per_block(N, H);
+    dim3 grid(ceil_div(H, rpb), N);
+    stats_kernel<<<grid, 256, 0, st>>>(a, b, f, H, W, rpb, ws.partial, ws.counters, out, ostride);
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
+}
+
+// =============================================================================== histograms
+// Bin rule of torch.histc(im, 256, 0, 256) and np.histogram2d(.., 256, ((0,256),(0,256)))
+// (metric.py:113, 141-143): bin = floor(v) for 0 <= v < 256, v == 256 -> 255, -0.0 -> 0,
+// anything else (v < 0, v > 256, NaN) is dropped; a joint sample is dropped if either value is.
+__device__ __forceinline__ int hist_bin(float v) {
+    if (!(v >= 0.f && v <= 256.f)) return -1;
+    const int b = (int)v;
+    return b > 255 ? 255 : b;
+}
+
+// grid (4*S, N): CTA (g, s) owns rows [64g, 64g+64) of both joint histograms (2 x 64 KB of shared
+// memory, ATOMS throughput is bin-count independent: 7.6 atomics/clk/SM measured) and scans pixel
+// split s of the pair; every pixel is scanned by 4 CTAs (the pair stays in L2), counted by one.
+__global__ void __launch_bounds__(256)
+hist_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ F, long long P, int S,
+            uint32_t* counts, uint32_t* extra) {
+    extern __shared__ uint32_t sh[];            // [2][64*256]
+    uint32_t* ja = sh;
+    uint32_t* jb = sh + 64 * 256;
+    const int n = blockIdx.y, g = blockIdx.x & 3, s = blockIdx.x >> 2;
+    for (int i = threadIdx.x; i < 2 * 64 * 256; i += 256) sh[i] = 0u;
+    __syncthreads();
+    const float* a = A + (size_t)n * P; const float* b = Bm + (size_t)n * P; const float* f = F + (size_t)n * P;
+    uint32_t* ex = extra + (size_t)n * 768;     // [extra_a | extra_b | extra_f]
+    const long long p0 = P * s / S, p1 = P * (s + 1) / S;
+    for (long long p = p0 + threadIdx.x; p < p1; p += 256) {
+        const int ba = hist_bin(__ldg(a + p)), bb = hist_bin(__ldg(b + p)), bf = hist_bin(__ldg(f + p));
+        if (ba >= 0 && (ba >> 6) == g) {
+            if (bf >= 0) atomicAdd(&ja[(ba & 63) * 256 + bf], 1u);
+            else atomicAdd(&ex[ba], 1u);                    // a counted in its marginal only
+        }
+        if (bb >= 0 && (bb >> 6) == g) {
+            if (bf >= 0) atomicAdd(&jb[(bb & 63) * 256 + bf], 1u);
+            else atomicAdd(&ex[256 + bb], 1u);
+        }
+        if (g == 0 && ba < 0 && bf >= 0) atomicAdd(&ex[512 + bf], 1u);   // f marginal is derived from joint_af
+    }
+    __syncthreads();
+    uint32_t* cn = counts + (size_t)n * MMIF_HIST_WORDS;
+    uint32_t* dst_a = cn + 768 + g * 64 * 256;
+    uint32_t* dst_b = cn + 768 + 65536 + g * 64 * 256;
+    if (S == 1) {
+        for (int i = threadIdx.x; i < 64 * 256; i += 256) { dst_a[i] = ja[i]; dst_b[i] = jb[i]; }
+    } else {
+        for (int i = threadIdx.x; i < 64 * 256; i += 256) {
+            const uint32_t va = ja[i], vb = jb[i];
+            if (va) atomicAdd(&dst_a[i], va);
+            if (vb) atomicAdd(&dst_b[i], vb);
+        }
+    }
+}
+
+// grid (N): marginals from the joints (+ the dropped-partner extras), then the entropy family in
+// double from the integer counts.
+__global__ void __launch_bounds__(256)
+hist_finalize_kernel(uint32_t* counts, uint32_t* extra, long long P, double* ent, long long estride) {
+    __shared__ uint32_t ha[256], hb[256], hf[256];
+    __shared__ double red[7 * 8];
+    const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint32_t* cn = counts + (size_t)n * MMIF_HIST_WORDS;
+    const uint32_t* jaf = cn + 768;
+    const uint32_t* jbf = cn + 768 + 65536;
+    uint32_t* ex = extra + (size_t)n * 768;
+    const double invP = 1.0 / (double)P;
+    // column sums (f marginal) and joint entropies: thread t owns column t
+    uint32_t colf = 0;
+    double je_af = 0.0, je_bf = 0.0;
+    for (int i = 0; i < 256; ++i) {
+        const uint32_t va = jaf[i * 256 + t], vb = jbf[i * 256 + t];
+        colf += va;
+        if (va) { const double p = va * invP; je_af -= p * log2(p); }
+        if (vb) { const double p = vb * invP; je_bf -= p * log2(p); }
+    }
+    hf[t] = colf + ex[512 + t];
+    // row sums: warp w owns rows w, w+8, ...
+    for (int i = warp; i < 256; i += 8) {
+        uint32_t ra = 0, rb = 0;
+        for (int j = lane; j < 256; j += 32) { ra += jaf[i * 256 + j]; rb += jbf[i * 256 + j]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ra += __shfl_xor_sync(0xffffffffu, ra, o); rb += __shfl_xor_sync(0xffffffffu, rb, o); }
+        if (lane == 0) { ha[i] = ra + ex[i]; hb[i] = rb + ex[256 + i]; }
+    }
+    __syncthreads();
+    cn[t] = ha[t]; cn[256 + t] = hb[t]; cn[512 + t] = hf[t];
+    ex[t] = 0u; ex[256 + t] = 0u; ex[512 + t] = 0u;          // leave the workspace zeroed
+    if (!ent) return;
+    const double pa = ha[t] * invP, pb = hb[t] * invP, pf = hf[t] * invP;
+    double v[7];
+    v[0] = ha[t] ? -pa * log2(pa) : 0.0;                       // metric.py:119-125
+    v[1] = hb[t] ? -pb * log2(pb) : 0.0;
+    v[2] = hf[t] ? -pf * log2(pf) : 0.0;
+    v[3] = je_af; v[4] = je_bf;                                 // metric.py:148-154
+    v[5] = (ha[t] && hf[t]) ? pa * log2(pa / pf) : 0.0;         // metric.py:158-165
+    v[6] = (hb[t] && hf[t]) ? pb * log2(pb / pf) : 0.0;
+    double vv[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) vv[i] = v[i];
+    block_sum<7, 256>(vv, red);
+    if (t == 0) {
+        double* e = ent + (size_t)n * estride;
+        e[MMIF_EN_A] = vv[0]; e[MMIF_EN_B] = vv[1]; e[MMIF_EN_F] = vv[2];
+        e[MMIF_JE_AF] = vv[3]; e[MMIF_JE_BF] = vv[4];
+        e[MMIF_CE_AF] = vv[5]; e[MMIF_CE_BF] = vv[6];
+        const double mi_af = vv[0] + vv[2] - vv[3], mi_bf = vv[1] + vv[2] - vv[4];    // metric.py:179-188
+        e[MMIF_MI_AF] = mi_af; e[MMIF_MI_BF] = mi_bf;
+        e[MMIF_NMI_AF] = 2.0 * mi_af / (vv[0] + vv[2]);
+        e[MMIF_NMI_BF] = 2.0 * mi_bf / (vv[1] + vv[2]);
+        e[11] = 0.0;
+    }
+}
+
+int launch_hist(const float* a, const float* b, const float* f, int N, int H, int W, uint32_t* counts, double* ent,
+                long long estride, MetricWs& ws, cudaStream_t st) {
+    const long long P = (long long)H * W;
+    int S = 148 / (4 * N);
+    S = S < 1 ? 1 : (S > 16 ? 16 : S);
+    if (P < 65536) S = 1;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMIF_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
+        attr_done = true;
+    }
+    dim3 grid(4 * S, N);
+    hist_kernel<<<grid, 256, 2 * 64 * 256 * 4, st>>>(a, b, f, P, S, counts, ws.hist_extra);
+    MMIF_CUDA(cudaGetLastError());
+    hist_finalize_kernel<<<N, 256, 0, st>>>(counts, ws.hist_extra, P, ent, estride);
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
+}
+
+// =============================================================================== Qabf / Nabf / Labf
+// thread = column, marches down a chunk of rows with a 3-row sliding window (reflect borders):
+// Sobel strength/orientation of a, b, f, then the edge-preservation sums of metric.py:209-256.
+constexpr int kQK = 5;   // Sq, Sw, Sn (modified), Sl, Sn_unmodified
+
+__global__ void __launch_bounds__(128)
+qabf_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ F, int H, int W, int rpb,
+            float Lexp, double* partial, unsigned* counters, double* out, long long ostride) {
+    __shared__ double red[kQK * 4];
+    __shared__ int flag;
+    const int n = blockIdx.z;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x, nblk = gridDim.x * gridDim.y;
+    const size_t off = (size_t)n * H * W;
+    const float* img[3] = {A + off, Bm + off, F + off};
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int r0 = blockIdx.y * rpb, r1 = min(r0 + rpb, H);
+    double acc[kQK];
+#pragma unroll
+    for (int i = 0; i < kQK; ++i) acc[i] = 0.0;
+    if (c < W) {
+        const int cm = (c == 0) ? 1 : c - 1, cp = (c == W - 1) ? W - 2 : c + 1;
+        float dA[3], dB[3], sA[3], sB[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dA[k] = dB[k] = sA[k] = sB[k] = 0.f;
+        float s[kQK];
+#pragma unroll
+        for (int i = 0; i < kQK; ++i) s[i] = 0.f;
+        for (int r = r0 - 1; r <= r1; ++r) {
+            const int rr = (r < 0) ? -r : ((r >= H) ? 2 * H - 2 - r : r);
+            float gx[3], gy[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float* row = img[k] + (size_t)rr * W;
+                const float um = __ldg(row + cm), uc = __ldg(row + c), up = __ldg(row + cp);
+                const float d = up - um, sm = um + 2.f * uc + up;
+                gx[k] = dA[k] + 2.f * dB[k] + d;
+                gy[k] = sm - sA[k];
+                dA[k] = dB[k]; dB[k] = d; sA[k] = sB[k]; sB[k] = sm;
+            }
+            if (r >= r0 + 1) {            // gx/gy describe pixel row r-1
+                float g[3], al[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { g[k] = sqrtf(gx[k] * gx[k] + gy[k] * gy[k]); al[k] = atan2f(gy[k], gx[k]); }
+                float Q[2], w[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float mx = fmaxf(g[k], g[2]), mn = fminf(g[k], g[2]);
+                    float G = __fdiv_rn(mn, mx);
+                    if (G != G) G = 0.f;                                             // metric.py:214
+                    const float Aa = __fdiv_rn(fabsf(fabsf(al[k] - al[2]) - 1.5707963267948966f) * 2.f, 3.141592653589793f);
+                    const float Qg = __fdiv_rn(0.9994f, 1.f + expf(-15.f * (G - 0.5f)));   // metric.py:218,224
+                    const float Qa = __fdiv_rn(0.9879f, 1.f + expf(-22.f * (Aa - 0.8f)));  // metric.py:219,225
+                    Q[k] = Qg * Qa;
+                    w[k] = powf(g[k], Lexp);
+                }
+                const float gmax = fmaxf(g[0], g[1]);
+                const float lossw = (1.f - Q[0]) * w[0] + (1.f - Q[1]) * w[1];
+                s[0] += Q[0] * w[0] + Q[1] * w[1];
+                s[1] += w[0] + w[1];
+                if (g[2] > gmax) { s[2] += lossw; s[4] += (2.f - Q[0] - Q[1]) * (w[0] + w[1]); }
+                if (g[2] <= gmax) s[3] += lossw;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kQK; ++i) acc[i] = (double)s[i];
+    }
+    double t[kQK];
+    if (!block_finish<kQK, 128>(acc, red, &flag, partial, counters, n, blk, nblk, t)) return;
+    double* o = out + (size_t)n * ostride;
+    o[0] = t[0] / t[1]; o[1] = t[2] / t[1]; o[2] = t[3] / t[1]; o[3] = t[4] / t[1];
+}
+
+int launch_qabf(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out, long long ostride,
+                MetricWs& ws, cudaStream_t st) {
+    if (H < 2 || W < 2) { set_error("qabf: H and W must be >= 2 (reflect pad)"); return MMIF_E_SHAPE; }
+    dim3 grid(ceil_div(W, 128), ceil_div(H, kQabfRows), N);
+    qabf_kernel<<<grid, 128, 0, st>>>(a, b, f, H, W, kQabfRows, L, ws.partial, ws.counters, out, ostride);
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
+}
+
+// =============================================================================== TVLoss
+__global__ void __launch_bounds__(256)
+tv_kernel(const float* __restrict__ X, int H, int W, int rpb, int norm, float weight, long long NI, double* partial,
+          unsigned* counters, double* out) {
+    __shared__ double red[2 * 8];
+    __shared__ int flag;
+    const int n = blockIdx.y, blk = blockIdx.y * gridDim.x + blockIdx.x, nblk = gridDim.x * gridDim.y;
+    const float* x = X + (size_t)n * H * W;
+    const int r0 = blockIdx.x * rpb, r1 = min(r0 + rpb, H);
+    double acc[2] = {0.0, 0.0};
+    for (int c = threadIdx.x; c < W; c += 256) {
+        float sv = 0.f, sh = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const size_t p = (size_t)r * W + c;
+            const float v = __ldg(x + p);
+            if (r + 1 < H) sv += norm_val(__ldg(x + p + W) - v, norm);
+            if (c + 1 < W) sh += norm_val(__ldg(x + p + 1) - v, norm);
+        }
+        acc[0] += sv; acc[1] += sh;
+    }
+    double t[2];
+    // all images reduce into one scalar: use sample slot 0 with nblk = whole grid
+    if (!block_finish<2, 256>(acc, red, &flag, partial, counters, 0, blk, nblk, t)) return;
+    out[0] = (double)weight * (t[0] / ((double)NI * (H - 1) * W) + t[1] / ((double)NI * H * (W - 1)));   // loss.py:354-358
+}
+
+int launch_tv(const float* x, int N, int H, int W, int norm, float weight, double* out, MetricWs& ws, cudaStream_t st) {
+    if (H < 2 || W < 2) { set_error("tv: H and W must be >= 2"); return MMIF_E_SHAPE; }
+    const int rpb = stats_rows_per_block(N, H);
+    dim3 grid(ceil_div(H, rpb), N);
+    tv_kernel<<<grid, 256, 0, st>>>(x, H, W, rpb, norm, weight, (long long)N, ws.partial, ws.counters, out);
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
+}
+
+}  // namespace mmif

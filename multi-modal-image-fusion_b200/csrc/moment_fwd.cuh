@@ -115,7 +115,7 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
         mbar_fence_init();
     }
     __syncthreads();
-    const Shift sh = tile_shift(src.img[0], src.img[1], src.img[2], p.H, p.W, i0 + p.seg_rows / 2 + HALO / 2, j0 + kTWI / 2, p.taps);
+    const Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, i0, rows_out + HALO, j0, p.taps);
 
     ring_issue(sm, src, &map1, &map2, &mapy, 0);
     ring_issue(sm, src, &map1, &map2, &mapy, 1);

@@ -91,9 +91,11 @@ struct Shift {
     float2 ec;       // eps c            (multiplies mu_y')
     float ecy;       // eps cy           (multiplies mu_k')
     float2 eccs;     // eps c cy s
+    float rho;       // window-sum mismatch of the separable taps (Taps::wrho)
 };
-__device__ __forceinline__ Shift make_shift(float c1, float c2, float cy, float s, float eps) {
+__device__ __forceinline__ Shift make_shift(float c1, float c2, float cy, float s, float eps, float rho) {
     Shift h;
+    h.rho = rho;
     h.c = f2(c1, c2);
     h.cy = cy;
     h.sc = f2(s * c1, s * c2);
@@ -127,13 +129,14 @@ __device__ __forceinline__ Stats stats_from(const Moments& m, const Shift& h) {
     Stats s;
     s.mu = add2(m.mk, h.sc);
     s.muy = m.my + h.scy;
-    // vk = ekk - mk*mk - k1*mk - k0
+    // vk = ekk - mk*mk - k1*mk - k0  + rho (ekk - 2 mk^2)   [rho: rescale the separable window sum]
     float2 t = fma2(m.mk, add2(m.mk, h.k1), h.k0);        // mk*(mk+k1) + k0
-    s.vk = f2(m.ekk.x - t.x, m.ekk.y - t.y);
-    s.vy = m.eyy - fmaf(m.my, m.my + h.k1y, h.k0y);
-    // cov = eky - mk*my - (ec*my + ecy*mk + eccs)
+    const float2 r2 = bcast(h.rho);
+    s.vk = fma2(r2, fma2(muls(-2.f, m.mk), m.mk, m.ekk), f2(m.ekk.x - t.x, m.ekk.y - t.y));
+    s.vy = fmaf(h.rho, fmaf(-2.f * m.my, m.my, m.eyy), m.eyy - fmaf(m.my, m.my + h.k1y, h.k0y));
+    // cov = eky - mk*my - (ec*my + ecy*mk + eccs) + rho (eky - 2 mk my)
     float2 u = fma2(m.mk, bcast(m.my + h.ecy), fma2(h.ec, bcast(m.my), h.eccs));
-    s.cov = f2(m.eky.x - u.x, m.eky.y - u.y);
+    s.cov = fma2(r2, fma2(muls(-2.f * m.my, m.mk), bcast(1.f), m.eky), f2(m.eky.x - u.x, m.eky.y - u.y));
     return s;
 }
 
@@ -209,16 +212,39 @@ __device__ __forceinline__ Moments moments_of(const float2 (&a)[4]) {
     return m;
 }
 
-// Tile shift constants: the pixel nearest the middle of the CTA's region, per image.
-__device__ __forceinline__ Shift tile_shift(const float* x1, const float* x2, const float* y, int H, int W, int rmid, int cmid,
-                                            const Taps& tp) {
-    rmid = min(max(rmid, 0), H - 1);
-    cmid = min(max(cmid, 0), W - 1);
-    const size_t off = (size_t)rmid * W + cmid;
-    const float c1 = finite_or_zero(__ldg(x1 + off));
-    const float c2 = finite_or_zero(__ldg(x2 + off));
-    const float cy = finite_or_zero(__ldg(y + off));
-    return make_shift(c1, c2, cy, tp.wsum, tp.weps);
+// Tile shift constants, per image: the minimum of a 16 x 8 grid of samples of the CTA's region
+// [r0, r0+nr) x [c0, c0+128).  For non-negative data 0 <= c <= (most) v, so |v - c| <= |v|: the
+// rounding noise of the shifted moments (~1e-7 (v-c)^2) never exceeds that of the reference's
+// unshifted fp32 moments (~1e-7 v^2), dark flat regions (v == c) become exact, and the values of a
+// well-exposed tile shrink by its floor.  Must be called by all threads (one __syncthreads).
+__device__ __forceinline__ Shift tile_shift(Smem& sm, const float* x1, const float* x2, const float* y, int H, int W, int r0, int nr,
+                                            int c0, const Taps& tp) {
+    const int t = threadIdx.x;
+    int r = r0 + ((t >> 4) * nr) / 8 + nr / 16;
+    int c = c0 + (t & 15) * 8 + 4;
+    r = min(max(r, 0), H - 1);
+    c = min(max(c, 0), W - 1);
+    const size_t off = (size_t)r * W + c;
+    float v[3] = {__ldg(x1 + off), __ldg(x2 + off), __ldg(y + off)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!(fabsf(v[k]) <= 3.0e38f)) v[k] = 3.0e38f;       // ignore NaN / inf samples
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+    }
+    float* scratch = reinterpret_cast<float*>(sm.red);
+    if ((t & 31) == 0) { scratch[(t >> 5) * 3 + 0] = v[0]; scratch[(t >> 5) * 3 + 1] = v[1]; scratch[(t >> 5) * 3 + 2] = v[2]; }
+    __syncthreads();
+    float c3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float m = scratch[k];
+#pragma unroll
+        for (int w = 1; w < kNT / 32; ++w) m = fminf(m, scratch[w * 3 + k]);
+        c3[k] = (m < 3.0e38f) ? m : 0.f;
+    }
+    __syncthreads();
+    return make_shift(c3[0], c3[1], c3[2], tp.wsum, tp.weps, tp.wrho);
 }
 
 __device__ __forceinline__ float norm_val(float d, int norm) { return norm == MMIF_NORM_L1 ? fabsf(d) : d * d; }

@@ -123,7 +123,7 @@ def main():
                      RM.calc_Nabf(a.to(dt), b.to(dt), f.to(dt), modified=False).item(),
                      RM.calc_viff(a.to(dt), b.to(dt), f.to(dt), simple=True).item(),
                      RM.calc_mul_info(a.to(dt), f.to(dt)).item(),
-                     RM.calc_ssim(a.to(dt), f.to(dt), data_range=1.0).item(),
+                     RM.calc_ssim(a.to(dt) / 255.0, f.to(dt) / 255.0, data_range=1.0).item(),   # test.py:51-52 convention
                      RM.calc_psnr(RM.calc_mse(a.to(dt), f.to(dt)), root=True).item()]
             out[f'{name}/{tag}/extra'] = np.array(extra, dtype=np.float64)
         out[f'{name}/hist_a'] = torch.histc(a, 256, 0, 256).to(torch.int64).numpy()

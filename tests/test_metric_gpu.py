@@ -1,0 +1,149 @@
+"""GPU parity of the metric suite against the golden vectors of the real reference and the live
+oracle.  Histogram counts are compared bit-exactly; floating-point metrics with the dual gate of
+SURVEY.md 8(c) (gates.py)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gates
+from oracle import fusion_metric as OM
+
+pytestmark = pytest.mark.gpu
+MG = np.load(cases.HERE + '/metric_golden.npz')
+
+
+def _mods():
+    import mmif_b200  # noqa: F401
+    from mmif_b200.core import metric as MM
+    return MM
+
+
+def T(x, dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dt)
+
+
+def _dense(idx, cnt):
+    j = np.zeros(65536, np.int64)
+    j[idx] = cnt
+    return j.reshape(256, 256)
+
+
+def ref_row_via_dropins(MM, a, b, f):
+    """eval.py:29-75 written against the drop-in functions exactly as the reference script does."""
+    sd, ag, sf = MM.calc_std(f), MM.calc_ag(f), MM.calc_sf(f)
+    mse = (MM.calc_mse(a, f) + MM.calc_mse(b, f)) * 0.5
+    psnr = MM.calc_psnr(mse)
+    cc = (MM.calc_cc(a, f) + MM.calc_cc(b, f)) * 0.5
+    scd = MM.calc_scd(a, b, f)
+    en = MM.calc_entropy(f)
+    ce = MM.calc_cross_ent(a, f) + MM.calc_cross_ent(b, f)
+    mi = MM.calc_mul_info(a, f, normalized=True) + MM.calc_mul_info(b, f, normalized=True)
+    qabf, nabf, labf = MM.calc_Qabf(a, b, f, L=1.5, full=True)
+    ssim = (MM.calc_ssim(a, f) + MM.calc_ssim(b, f)) * 0.5
+    msssim = (MM.calc_msssim(a, f) + MM.calc_msssim(b, f)) * 0.5
+    viff = MM.calc_viff(a, b, f, simple=False)
+    assert mi.dtype == torch.float64 and sd.dtype == torch.float32 and sd.dim() == 0
+    vals = [sd, ag, sf, mse, psnr, cc, scd, en, ce, mi, qabf, nabf, labf, ssim, msssim, viff]
+    return [v.item() for v in vals]
+
+
+@pytest.mark.parametrize('name', cases.METRIC_CASES)
+@pytest.mark.parametrize('where', ['cuda', 'cpu'])
+def test_dropin_functions_vs_golden(name, where):
+    """CPU inputs are what eval.py really passes (eval.py:198-200); CUDA inputs what test.py passes."""
+    MM = _mods()
+    a, b, f = (T(x).to(where) for x in cases.metric_case(name))
+    got = ref_row_via_dropins(MM, a, b, f)
+    r32, r64 = MG[f'{name}/f32/metrics'], MG[f'{name}/f64/metrics']
+    for k, nm in enumerate(OM.METRIC_NAMES):
+        gates.assert_scalar(f'{name}/{nm}', got[k], r32[k], r64[k])
+
+
+@pytest.mark.parametrize('name', cases.METRIC_CASES)
+def test_fused_suite_vs_golden_and_extras(name):
+    MM = _mods()
+    a, b, f = (T(x).cuda() for x in cases.metric_case(name))
+    row = MM.eval_metrics(a, b, f)
+    r32, r64 = MG[f'{name}/f32/metrics'], MG[f'{name}/f64/metrics']
+    for k, nm in enumerate(OM.METRIC_NAMES):
+        gates.assert_scalar(f'{name}/suite/{nm}', row[nm], r32[k], r64[k])
+    extra = [MM.calc_mean(f).item(), MM.calc_Nabf(a, b, f, modified=False).item(), MM.calc_viff(a, b, f, simple=True).item(),
+             MM.calc_mul_info(a, f).item(), MM.calc_ssim(a / 255.0, f / 255.0, data_range=1.0).item(),
+             MM.calc_psnr(MM.calc_mse(a, f), root=True).item()]
+    e32, e64 = MG[f'{name}/f32/extra'], MG[f'{name}/f64/extra']
+    for k, nm in enumerate(('mean', 'nabf_unmodified', 'viff_simple', 'mi_raw', 'ssim_L1', 'psnr_root')):
+        gates.assert_scalar(f'{name}/{nm}', extra[k], e32[k], e64[k])
+
+
+@pytest.mark.parametrize('name', cases.METRIC_CASES)
+def test_histograms_bit_exact(name):
+    MM = _mods()
+    a, b, f = (T(x).cuda() for x in cases.metric_case(name))
+    ha, hb, hf, jaf, jbf = MM.histograms(a, b, f)
+    assert np.array_equal(ha.numpy(), MG[f'{name}/hist_a'])
+    assert np.array_equal(hb.numpy(), MG[f'{name}/hist_b'])
+    assert np.array_equal(hf.numpy(), MG[f'{name}/hist_f'])
+    assert np.array_equal(jaf.numpy(), _dense(MG[f'{name}/joint_af_idx'], MG[f'{name}/joint_af_cnt']))
+    assert np.array_equal(jbf.numpy(), _dense(MG[f'{name}/joint_bf_idx'], MG[f'{name}/joint_bf_cnt']))
+
+
+def test_histogram_edge_rule_bit_exact():
+    """value 256.0 -> bin 255, -0.0 -> bin 0, <0 / >256 / NaN / inf dropped (pair dropped if either is)."""
+    MM = _mods()
+    v, w = (T(x).cuda() for x in cases.hist_edge_vector())
+    hv, _, hw, jvw, _ = MM.histograms(v, v, w)
+    assert np.array_equal(hv.numpy(), MG['hist_edge/hist_v'])
+    assert np.array_equal(hw.numpy(), MG['hist_edge/hist_w'])
+    assert np.array_equal(jvw.numpy(), _dense(MG['hist_edge/joint_idx'], MG['hist_edge/joint_cnt']))
+
+
+@pytest.mark.parametrize('shape', [(480, 640), (1024, 1224)])
+def test_config_shapes_vs_live_oracle(shape):
+    """BASELINE configs 3 / 4 shapes (640x480 TNO, 1224x1024 polarization), integer-valued images."""
+    MM = _mods()
+    g = torch.Generator().manual_seed(shape[0])
+    a = torch.randint(0, 256, (1, 1) + shape, generator=g).float()
+    b = torch.randint(0, 256, (1, 1) + shape, generator=g).float()
+    f = torch.floor((a + b) / 2)
+    r32 = OM.eval_pair(a, b, f)
+    r64 = OM.eval_pair(a.double(), b.double(), f.double())
+    row = MM.eval_metrics(a.cuda(), b.cuda(), f.cuda())
+    for nm in OM.METRIC_NAMES:
+        gates.assert_scalar(f'{shape}/{nm}', row[nm], r32[nm], r64[nm])
+    ha, hb, hf, jaf, jbf = MM.histograms(a.cuda(), b.cuda(), f.cuda())
+    assert np.array_equal(hf.numpy(), OM.hist_counts(f).to(torch.int64).numpy())
+    assert np.array_equal(jaf.numpy(), OM.joint_counts(a, f).numpy().astype(np.int64))
+    assert np.array_equal(jbf.numpy(), OM.joint_counts(b, f).numpy().astype(np.int64))
+    assert int(ha.sum()) == a.numel() and int(jaf.sum()) == a.numel()
+
+
+def test_batched_suite_equals_per_pair_and_is_deterministic():
+    MM = _mods()
+    g = torch.Generator().manual_seed(11)
+    a = torch.randint(0, 256, (5, 1, 120, 200), generator=g).float().cuda()
+    b = torch.randint(0, 256, (5, 1, 120, 200), generator=g).float().cuda()
+    f = torch.maximum(a, b)
+    rows = MM.eval_metrics_batch(a, b, f)
+    rows2 = MM.eval_metrics_batch(a, b, f)
+    assert torch.equal(rows, rows2)
+    for n in range(5):
+        one = MM.eval_metrics_batch(a[n:n + 1], b[n:n + 1], f[n:n + 1])[0]
+        np.testing.assert_allclose(rows[n].cpu().numpy(), one.cpu().numpy(), rtol=1e-7, atol=1e-12)  # row blocking differs with N
+
+
+def test_constant_images_and_errors():
+    """sigma = 0 paths: cc is 0/0 = nan in the reference too; Qabf 0/0 -> 0 weights; VIF eps branches."""
+    MM = _mods()
+    a = torch.full((1, 1, 64, 64), 100.0)
+    b = torch.full((1, 1, 64, 64), 50.0)
+    f = torch.full((1, 1, 64, 64), 75.0)
+    r32 = OM.eval_pair(a, b, f)
+    r64 = OM.eval_pair(a.double(), b.double(), f.double())
+    row = MM.eval_metrics(a.cuda(), b.cuda(), f.cuda())
+    for nm in ('sd', 'ag', 'sf', 'mse', 'psnr', 'en', 'ce', 'ssim', 'msssim'):
+        gates.assert_scalar(f'const/{nm}', row[nm], r32[nm], r64[nm])
+    for nm in ('cc', 'scd', 'qabf', 'nabf', 'labf'):
+        assert np.isnan(row[nm]) == np.isnan(r32[nm]), (nm, row[nm], r32[nm])
+    with pytest.raises(Exception):
+        MM.calc_viff(torch.rand(1, 1, 20, 20).cuda(), torch.rand(1, 1, 20, 20).cuda(), torch.rand(1, 1, 20, 20).cuda())

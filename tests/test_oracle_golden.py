@@ -66,7 +66,7 @@ def test_metric_suite(name, tag):
     got = np.array([r[k] for k in OM.METRIC_NAMES])
     np.testing.assert_allclose(got, MG[f'{name}/{tag}/metrics'], rtol=1e-6 if tag == 'f32' else 1e-12, atol=1e-9)
     extra = [OM.mean(f).item(), OM.nabf(a, b, f, modified=False).item(), OM.viff(a, b, f, simple=True).item(),
-             OM.mutual_info(a, f).item(), OM.ssim(a, f, data_range=1.0).item(),
+             OM.mutual_info(a, f).item(), OM.ssim(a / 255.0, f / 255.0, data_range=1.0).item(),
              OM.psnr(OM.mse(a, f), root=True).item()]
     np.testing.assert_allclose(extra, MG[f'{name}/{tag}/extra'], rtol=1e-6 if tag == 'f32' else 1e-12, atol=1e-9)
 
