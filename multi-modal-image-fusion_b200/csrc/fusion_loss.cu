@@ -46,18 +46,27 @@ struct BwdParams {
 constexpr int kCPitch = 2 * kTWI + 2;   // float2 units per coefficient row (2 pair-maps x 128 + 16 B pad)
 constexpr int kTMC = 112;               // tmaps / gbuf columns
 
+constexpr int kRPB = kTWI + 4;           // backward ring row pitch (132 floats = 16 mod 128 B)
+using SmemB = SmemT<4, kRPB>;
+
+// r * sign(g) with sign(0) = 0 (torch.sign / autograd of abs at 0)
+__device__ __forceinline__ float mulsign(float r, float g) {
+    return (g == 0.f) ? 0.f : __int_as_float(__float_as_int(r) ^ (__float_as_int(g) & 0x80000000));
+}
+
 struct SmemBwd {
-    Smem s;                              // ring + vbuf (vbuf also hosts tmaps and the B1->B2 buffer)
+    SmemB s;                             // ring + vbuf (vbuf also hosts the B1->B2 buffer)
     alignas(16) float2 cbuf[kRB * kCPitch];          // coefficient rows of the current batch: (a,b) and (c1,c2)
-    float gbuf[kRB][kTMC];               // pixel + Sobel gradient of the batch rows
+    alignas(16) float gbuf[kRB][kTMC + 4];   // pixel + Sobel gradient of the batch rows (row pitch 464 B = 80 mod 128)
 };
 
+template <bool FAST>      // FAST: mode='max' + 'l1' for both terms (train.py:67-68,307-308), no run-time mode switches
 __global__ void __launch_bounds__(kNT, 2)
 fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemBwd& sb = *reinterpret_cast<SmemBwd*>(smem_raw);
-    Smem& sm = sb.s;
+    SmemB& sm = sb.s;
     const int strip = blockIdx.x, seg = blockIdx.y, n = blockIdx.z;
     const int j0 = strip * kTG, i0 = seg * p.seg_rows;
     const int jw0 = j0 - kOFF;             // first window / input column of the tile (multiple of 4: TMA)
@@ -94,117 +103,80 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
 
     const int lane = t & 31, warp = t >> 5;
     const int ho = lane & 7, hg = warp * 4 + (lane >> 3);
-    float2* tmaps = sm.vbuf;                          // [10][kTMC] (tx,ty), alive between S1 and S2
     float2* tbuf = sm.vbuf;                           // [8][2][128]+pad, alive between B1 and B2
     float2 carry[HALO][2];                            // vertical adjoint state: pending gradient rows
 #pragma unroll
     for (int d = 0; d < HALO; ++d) carry[d][0] = carry[d][1] = f2(0.f, 0.f);
 
+    // Sobel-adjoint phase: column of this thread and its sliding state
+    const int s_ci = 30 * warp + lane - 1;            // column relative to j0: -1 .. 120 (lanes 0 / 31 are halo lanes)
+    const int s_c = j0 + s_ci;
+    const bool s_colok = (s_c >= 0) && (s_c < p.W) && (s_ci <= kTG);
+    const bool s_own = (lane >= 1) && (lane <= 30) && (s_ci >= 0) && (s_ci < kTG) && (s_c < jend);
+    const int s_cc = min(max(s_c, 0), p.W - 1);
+    const int s_t0 = min(s_cc - jw0, kRPB - 1);
+    const int s_tm = min(((s_cc == 0) ? 1 : s_cc - 1) - jw0, kRPB - 1);
+    const int s_tp = min(((s_cc == p.W - 1) ? p.W - 2 : s_cc + 1) - jw0, kRPB - 1);
+    float2 s_dA = f2(0.f, 0.f), s_dB = s_dA, s_sA = s_dA, s_sB = s_dA, s_ucA = s_dA, s_ucB = s_dA;
+    float s_dAy = 0.f, s_dBy = 0.f, s_sAy = 0.f, s_sBy = 0.f, s_ucAy = 0.f, s_ucBy = 0.f;
+    float s_hxA = 0.f, s_hxB = 0.f, s_vyA = 0.f, s_vyB = 0.f;
+
     for (int b = 0; b < nb; ++b) {
         const int Rb = R0 + b * kRB;                  // first gradient row of this batch
         ring_wait(sm, src, b + 2);
         const bool emit = (Rb + kRB > i0);            // any owned gradient row in this batch
-        // ---------------- S1: tx, ty on rows [Rb-1, Rb+9) x cols [j0-1, j0+109) ----------------
-        if (emit) {
-            if (t < kTG + 2) {
-                const int c = j0 - 1 + t;
-                const bool cvalid = (c >= 0) && (c < p.W);
-                const int cc = min(max(c, 0), p.W - 1);
-                const int t0 = cc - jw0;
-                const int tmc = ((cc == 0) ? 1 : cc - 1) - jw0;
-                const int tpc = ((cc == p.W - 1) ? p.W - 2 : cc + 1) - jw0;
-                float dA[3], dB[3], sA[3], sB[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) dA[k] = dB[k] = sA[k] = sB[k] = 0.f;
-                const int lr_lo = b * kRB - 2, lr_hi = b * kRB + 17;   // ring-local rows present
-                for (int q = Rb - 2; q <= Rb + 9; ++q) {
-                    int rr = (q < 0) ? -q : ((q >= p.H) ? 2 * p.H - 2 - q : q);
-                    int lr = min(max(rr - R0, lr_lo), lr_hi) & (kRingRows - 1);
-                    float gx[3], gy[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float um = sm.ring[k][lr][tmc];
-                        const float uc = sm.ring[k][lr][t0];
-                        const float up = sm.ring[k][lr][tpc];
-                        const float d = up - um;
-                        const float s = um + 2.f * uc + up;
-                        gx[k] = dA[k] + 2.f * dB[k] + d;
-                        gy[k] = s - sA[k];
-                        dA[k] = dB[k]; dB[k] = d; sA[k] = sB[k]; sB[k] = s;
-                    }
-                    if (q >= Rb) {                     // gx/gy describe row q-1 in [Rb-1, Rb+9)
-                        const int qr = q - 1;
-                        float2 txy = f2(0.f, 0.f);
-                        if (cvalid && qr >= 0 && qr < p.H) {
-                            const float S1 = fabsf(gx[0]) + fabsf(gy[0]);
-                            const float S2 = fabsf(gx[1]) + fabsf(gy[1]);
-                            const float Sy = fabsf(gx[2]) + fabsf(gy[2]);
-                            float r;
-                            if (p.grad_combine == MMIF_COMBINE_MAX) r = k_grad * norm_der(Sy - fmaxf(S1, S2), p.grad_norm);
-                            else r = k_grad * (norm_der(Sy - S1, p.grad_norm) + norm_der(Sy - S2, p.grad_norm));
-                            txy = f2(r * sgn(gx[2]), r * sgn(gy[2]));
-                        }
-                        tmaps[(qr - (Rb - 1)) * kTMC + t] = txy;
-                    }
+        if (b + 1 < nb) ring_issue(sm, src, &map1, &map2, &mapy, b + 3);   // slot of group b-1: nobody reads it any more
+        // ---------------- S: Sobel + pixel adjoint of gradient rows [Rb, Rb+8) -> gbuf ------------
+        // thread = column (warps own 30 columns + 1 halo lane each side); one input row per step:
+        // input row q' -> Sobel / tx,ty of row q'-1 -> (neighbour columns by shuffle) -> G of row q'-2.
+        // All sliding state lives in registers across batches, so every input row is visited once.
+        {
+#pragma unroll 2
+            for (int step = 0; step < kRB; ++step) {
+                const int qp = Rb + 2 + step;                       // input row q'
+                int rr = (qp < 0) ? -qp : ((qp >= p.H) ? 2 * p.H - 2 - qp : qp);
+                const int lr = min(max(rr - R0, b * kRB), b * kRB + 3 * kRB - 1) & (SmemB::kRows - 1);
+                const float2 um = f2(sm.ring[0][lr][s_tm], sm.ring[1][lr][s_tm]);
+                const float2 uc = f2(sm.ring[0][lr][s_t0], sm.ring[1][lr][s_t0]);
+                const float2 up = f2(sm.ring[0][lr][s_tp], sm.ring[1][lr][s_tp]);
+                const float umy = sm.ring[2][lr][s_tm], ucy = sm.ring[2][lr][s_t0], upy = sm.ring[2][lr][s_tp];
+                const float2 d = fma2(bcast(-1.f), um, up);
+                const float2 sv = fma2(bcast(2.f), uc, add2(um, up));
+                const float2 gx = fma2(bcast(2.f), s_dB, add2(s_dA, d));   // Sobel of row q'-1
+                const float2 gy = fma2(bcast(-1.f), s_sA, sv);
+                const float dy = upy - umy;
+                const float sy = fmaf(2.f, ucy, umy + upy);
+                const float gxy = fmaf(2.f, s_dBy, s_dAy + dy);
+                const float gyy = sy - s_sAy;
+                const int qt = qp - 1;
+                float tx = 0.f, ty = 0.f;
+                if (s_colok && qt >= 0 && qt < p.H) {
+                    const float S1 = fabsf(gx.x) + fabsf(gy.x), S2 = fabsf(gx.y) + fabsf(gy.y), Sy = fabsf(gxy) + fabsf(gyy);
+                    float r;
+                    if (FAST) r = mulsign(k_grad, Sy - fmaxf(S1, S2));
+                    else if (p.grad_combine == MMIF_COMBINE_MAX) r = k_grad * norm_der(Sy - fmaxf(S1, S2), p.grad_norm);
+                    else r = k_grad * (norm_der(Sy - S1, p.grad_norm) + norm_der(Sy - S2, p.grad_norm));
+                    tx = mulsign(r, gxy);
+                    ty = mulsign(r, gyy);
                 }
+                const float txl = __shfl_up_sync(0xffffffffu, tx, 1), txr = __shfl_down_sync(0xffffffffu, tx, 1);
+                const float tyl = __shfl_up_sync(0xffffffffu, ty, 1), tyr = __shfl_down_sync(0xffffffffu, ty, 1);
+                float hx = txl - txr, vy = tyl + 2.f * ty + tyr;
+                if (s_c == 1) { hx -= txl; vy += tyl; }                 // column -1 folds onto column 1
+                if (s_c == p.W - 2) { hx += txr; vy += tyr; }           // column W folds onto column W-2
+                const int gi = qp - 2;                                  // gradient row completed by this step
+                float G = s_hxA + 2.f * s_hxB + hx + s_vyA - vy;
+                if (gi == 1) G += s_hxA - s_vyA;                        // row -1 folds onto row 1
+                if (gi == p.H - 2) G += hx + vy;                        // row H folds onto row H-2
+                if (FAST) G += mulsign(k_pix, s_ucAy - fmaxf(s_ucA.x, s_ucA.y));
+                else if (p.pixel_combine == MMIF_COMBINE_MAX) G += k_pix * norm_der(s_ucAy - fmaxf(s_ucA.x, s_ucA.y), p.pixel_norm);
+                else G += k_pix * (norm_der(s_ucAy - s_ucA.x, p.pixel_norm) + norm_der(s_ucAy - s_ucA.y, p.pixel_norm));
+                if (s_own && gi >= i0 && gi < iend) sb.gbuf[step][s_ci] = G;
+                s_dA = s_dB; s_dB = d; s_sA = s_sB; s_sB = sv; s_dAy = s_dBy; s_dBy = dy; s_sAy = s_sBy; s_sBy = sy;
+                s_hxA = s_hxB; s_hxB = hx; s_vyA = s_vyB; s_vyB = vy;
+                s_ucA = s_ucB; s_ucB = uc; s_ucAy = s_ucBy; s_ucBy = ucy;
             }
         }
-        __syncthreads();
-        // ---------------- S2: folded Sobel adjoint + pixel term -> gbuf ------------------------
-        if (emit && t < kTG) {
-            const int j = j0 + t;
-            auto tmget = [&](int qi, int qj) -> float2 {   // bounds-checked (border folds only)
-                const int ri = qi - (Rb - 1), ci = qj - (j0 - 1);
-                if (ri < 0 || ri >= 10 || ci < 0 || ci >= kTG + 2) return f2(0.f, 0.f);
-                return tmaps[ri * kTMC + ci];
-            };
-            auto Gslow = [&](int pi, int pj) -> float {
-                float g = 0.f;
-#pragma unroll
-                for (int dr = -1; dr <= 1; ++dr) {
-                    const float sv = (dr == 0) ? 2.f : 1.f;
-                    g += sv * (tmget(pi + dr, pj - 1).x - tmget(pi + dr, pj + 1).x);
-                }
-#pragma unroll
-                for (int dc = -1; dc <= 1; ++dc) {
-                    const float shh = (dc == 0) ? 2.f : 1.f;
-                    g += shh * (tmget(pi - 1, pj + dc).y - tmget(pi + 1, pj + dc).y);
-                }
-                return g;
-            };
-            for (int o = 0; o < kRB; ++o) {
-                const int i = Rb + o;
-                float g = 0.f;
-                if (i >= i0 && i < iend && j < jend) {
-                    const float2* r0 = tmaps + (o + 0) * kTMC + t;     // row i-1, col j-1
-                    const float2* r1 = tmaps + (o + 1) * kTMC + t;     // row i
-                    const float2* r2 = tmaps + (o + 2) * kTMC + t;     // row i+1
-                    const float2 a0 = r0[0], a1 = r0[1], a2 = r0[2];
-                    const float2 b0 = r1[0], b2 = r1[2];
-                    const float2 c0 = r2[0], c1 = r2[1], c2 = r2[2];
-                    g = (a0.x - a2.x) + 2.f * (b0.x - b2.x) + (c0.x - c2.x)
-                      + (a0.y + 2.f * a1.y + a2.y) - (c0.y + 2.f * c1.y + c2.y);
-                    const bool ftop = (i == 1), fbot = (i == p.H - 2), fl = (j == 1), fr = (j == p.W - 2);
-                    if (ftop | fbot | fl | fr) {
-                        if (ftop) g += Gslow(-1, j);
-                        if (fbot) g += Gslow(p.H, j);
-                        if (fl) g += Gslow(i, -1);
-                        if (fr) g += Gslow(i, p.W);
-                        if (ftop && fl) g += Gslow(-1, -1);
-                        if (ftop && fr) g += Gslow(-1, p.W);
-                        if (fbot && fl) g += Gslow(p.H, -1);
-                        if (fbot && fr) g += Gslow(p.H, p.W);
-                    }
-                    const int lr = (b * kRB + o) & (kRingRows - 1);
-                    const float u1 = sm.ring[0][lr][t + kOFF], u2 = sm.ring[1][lr][t + kOFF], uy = sm.ring[2][lr][t + kOFF];
-                    if (p.pixel_combine == MMIF_COMBINE_MAX) g += k_pix * norm_der(uy - fmaxf(u1, u2), p.pixel_norm);
-                    else g += k_pix * (norm_der(uy - u1, p.pixel_norm) + norm_der(uy - u2, p.pixel_norm));
-                }
-                sb.gbuf[o][t] = g;
-            }
-        }
-        __syncthreads();
-        if (b + 1 < nb) ring_issue(sm, src, &map1, &map2, &mapy, b + 3);
         // ---------------- A1: vertical moments of window rows [Rb, Rb+8) ------------------------
         vpass_moments<WIN>(sm, p.taps, sh, (b & 3) * kRB);
         __syncthreads();
@@ -295,16 +267,30 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                 float2 acc[8][2];
                 // gradient column g sums window columns [g + kOFF - HALO, g + kOFF] of the tile
                 hpass<WIN, 2, true>(tbuf + ho * kCPitch + hg * 8 + (kOFF - HALO), kTWI, p.taps, acc);
-                const int lr = (b * kRB + ho) & (kRingRows - 1);
-                float outv[8];
+                const int lr = (b * kRB + ho) & (SmemB::kRows - 1);
+                float outv[8], u1[8], u2[8], uy[8], gb[8];
+                {   // 8 pixels of row lr: LDS.128, lanes 0-7 are 8 ring rows (pitch = 16 mod 128 B)
+                    const int tc = kOFF + hg * 8;
+                    const float4* q1 = reinterpret_cast<const float4*>(&sm.ring[0][lr][tc]);
+                    const float4* q2 = reinterpret_cast<const float4*>(&sm.ring[1][lr][tc]);
+                    const float4* qy = reinterpret_cast<const float4*>(&sm.ring[2][lr][tc]);
+                    const float4* qg = reinterpret_cast<const float4*>(&sb.gbuf[ho][hg * 8]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a = q1[h], bq = q2[h], c = qy[h], g4 = qg[h];
+                        u1[4 * h] = a.x; u1[4 * h + 1] = a.y; u1[4 * h + 2] = a.z; u1[4 * h + 3] = a.w;
+                        u2[4 * h] = bq.x; u2[4 * h + 1] = bq.y; u2[4 * h + 2] = bq.z; u2[4 * h + 3] = bq.w;
+                        uy[4 * h] = c.x; uy[4 * h + 1] = c.y; uy[4 * h + 2] = c.z; uy[4 * h + 3] = c.w;
+                        gb[4 * h] = g4.x; gb[4 * h + 1] = g4.y; gb[4 * h + 2] = g4.z; gb[4 * h + 3] = g4.w;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int tc = kOFF + hg * 8 + j;
-                    const float x1s = sm.ring[0][lr][tc] - sh.c.x;
-                    const float x2s = sm.ring[1][lr][tc] - sh.c.y;
-                    const float ys = sm.ring[2][lr][tc] - sh.cy;
+                    const float x1s = u1[j] - sh.c.x;
+                    const float x2s = u2[j] - sh.c.y;
+                    const float ys = uy[j] - sh.cy;
                     const float dS = acc[j][0].x + 2.f * ys * acc[j][0].y + x1s * acc[j][1].x + x2s * acc[j][1].y;
-                    outv[j] = fmaf(k_ssim, dS, sb.gbuf[ho][hg * 8 + j]);
+                    outv[j] = fmaf(k_ssim, dS, gb[j]);
                 }
                 float* dst = p.dF + img_off + (size_t)i * p.W + j0 + hg * 8;
                 if (p.vec_store && j0 + hg * 8 + 8 <= jend) {
@@ -392,16 +378,20 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     p.w_ssim = cfg->w_ssim; p.w_pixel = cfg->w_pixel; p.w_grad = cfg->w_grad;
     p.vec_store = ((W & 3) == 0) && ((((uintptr_t)dF) & 15) == 0);
     CUtensorMap m1, m2, my;
-    p.use_tma = make_tensor_map(&m1, i1, B, H, W, kTWI, kRB) && make_tensor_map(&m2, i2, B, H, W, kTWI, kRB) &&
-                make_tensor_map(&my, f, B, H, W, kTWI, kRB);
+    p.use_tma = make_tensor_map(&m1, i1, B, H, W, kRPB, kRB) && make_tensor_map(&m2, i2, B, H, W, kRPB, kRB) &&
+                make_tensor_map(&my, f, B, H, W, kRPB, kRB);
     if (!p.use_tma) { memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2)); memset(&my, 0, sizeof(my)); }
     static bool attr_done = false;
     if (!attr_done) {
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd)));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd)));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd)));
         attr_done = true;
     }
     dim3 grid(g.nstrip, g.nseg, B);
-    fusion_loss_bwd_kernel<<<grid, kNT, sizeof(SmemBwd), (cudaStream_t)stream>>>(m1, m2, my, p);
+    const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
+                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
+    if (fast) fusion_loss_bwd_kernel<true><<<grid, kNT, sizeof(SmemBwd), (cudaStream_t)stream>>>(m1, m2, my, p);
+    else fusion_loss_bwd_kernel<false><<<grid, kNT, sizeof(SmemBwd), (cudaStream_t)stream>>>(m1, m2, my, p);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }

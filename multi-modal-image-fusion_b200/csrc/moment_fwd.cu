@@ -34,10 +34,10 @@ static int launch_t(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensor
                     cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        MMIF_CUDA(cudaFuncSetAttribute(moment_fwd_kernel<WIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        MMIF_CUDA(cudaFuncSetAttribute(moment_fwd_kernel<WIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
         attr_done = true;
     }
-    moment_fwd_kernel<WIN, EPI><<<grid, kNT, sizeof(Smem), st>>>(m1, m2, my, p);
+    moment_fwd_kernel<WIN, EPI><<<grid, kNT, sizeof(SmemF), st>>>(m1, m2, my, p);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }

@@ -44,7 +44,10 @@ struct FwdParams {
 static inline size_t ws_counters_bytes(int B) { return (size_t)(((B + 1) * 4 + 255) / 256) * 256; }
 
 // --- forward Sobel / pixel terms for the pixel rows a batch owns (thread = column) ----------
-__device__ __forceinline__ void fwd_sobel_pixel(const Smem& sm, const FwdParams& p, int i0, int j0, int rlo, int rhi, int clo,
+using SmemF = SmemT<3, kTWI>;   // forward kernels: 3-slot ring, 72 KB per CTA -> 3 CTAs per SM
+
+template <class SM>
+__device__ __forceinline__ void fwd_sobel_pixel(const SM& sm, const FwdParams& p, int i0, int j0, int rlo, int rhi, int clo,
                                                 int chi, float& pix_sum, float& grad_sum) {
     const int c = j0 + (int)threadIdx.x;
     if (c < clo || c >= chi) return;
@@ -56,7 +59,7 @@ __device__ __forceinline__ void fwd_sobel_pixel(const Smem& sm, const FwdParams&
     for (int k = 0; k < 3; ++k) dA[k] = dB[k] = sA[k] = sB[k] = u0p[k] = 0.f;
     for (int r = rlo - 1; r <= rhi; ++r) {
         const int rr = (r < 0) ? -r : ((r >= p.H) ? 2 * p.H - 2 - r : r);
-        const int lr = (rr - i0) & (kRingRows - 1);
+        const int lr = SM::wrap_any(rr - i0);
         float S[3], u0[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -86,18 +89,56 @@ __device__ __forceinline__ void fwd_sobel_pixel(const Smem& sm, const FwdParams&
     }
 }
 
+// Same terms for the training configuration (mode='max', 'l1': train.py:67-68,307-308) without the
+// run-time mode switches; the two sources are processed as one packed (x1, x2) pair.
+template <class SM>
+__device__ __forceinline__ void fwd_sobel_pixel_fast(const SM& sm, int H, int W, int i0, int j0, int rlo, int rhi, int clo,
+                                                     int chi, float& pix_sum, float& grad_sum) {
+    const int c = j0 + (int)threadIdx.x;
+    if (c < clo || c >= chi) return;
+    const int t0 = threadIdx.x;
+    const int tm = ((c == 0) ? 1 : c - 1) - j0;
+    const int tp = ((c == W - 1) ? W - 2 : c + 1) - j0;
+    float2 dA = f2(0.f, 0.f), dB = dA, sA = dA, sB = dA, ucp = dA;
+    float dAy = 0.f, dBy = 0.f, sAy = 0.f, sBy = 0.f, ucpy = 0.f;
+    const float2 two = bcast(2.f), neg1 = bcast(-1.f);
+    for (int r = rlo - 1; r <= rhi; ++r) {
+        const int rr = (r < 0) ? -r : ((r >= H) ? 2 * H - 2 - r : r);
+        const int lr = SM::wrap_any(rr - i0);
+        const float2 um = f2(sm.ring[0][lr][tm], sm.ring[1][lr][tm]);
+        const float2 uc = f2(sm.ring[0][lr][t0], sm.ring[1][lr][t0]);
+        const float2 up = f2(sm.ring[0][lr][tp], sm.ring[1][lr][tp]);
+        const float umy = sm.ring[2][lr][tm], ucy = sm.ring[2][lr][t0], upy = sm.ring[2][lr][tp];
+        const float2 d = fma2(neg1, um, up);
+        const float2 s = fma2(two, uc, add2(um, up));
+        const float2 gx = fma2(two, dB, add2(dA, d));
+        const float2 gy = fma2(neg1, sA, s);
+        const float dy = upy - umy;
+        const float sy = fmaf(2.f, ucy, umy + upy);
+        const float gxy = fmaf(2.f, dBy, dAy + dy);
+        const float gyy = sy - sAy;
+        if (r >= rlo + 1) {                      // the sums describe pixel row r-1
+            const float S1 = fabsf(gx.x) + fabsf(gy.x), S2 = fabsf(gx.y) + fabsf(gy.y), Sy = fabsf(gxy) + fabsf(gyy);
+            grad_sum += fabsf(Sy - fmaxf(S1, S2));
+            pix_sum += fabsf(ucpy - fmaxf(ucp.x, ucp.y));
+        }
+        dA = dB; dB = d; sA = sB; sB = s; ucp = uc;
+        dAy = dBy; dBy = dy; sAy = sBy; sBy = sy; ucpy = ucy;
+    }
+}
+
 // log2(1+x), accurate for small x (the reference's fp32 log2(1 + x) loses x's low bits; its fp64
 // evaluation does not — stay near the fp64 value).
 __device__ __forceinline__ float log2_1p(float x) { return log1pf(x) * 1.4426950408889634f; }
 
 template <int WIN, int EPI>
-__global__ void __launch_bounds__(kNT, 2)
+__global__ void __launch_bounds__(kNT, 3)
 moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                   const __grid_constant__ CUtensorMap mapy, const FwdParams p) {
     constexpr int HALO = FwdGeo<WIN>::HALO;
     constexpr int TWO = FwdGeo<WIN>::TWO;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
     const int strip = blockIdx.x, seg = blockIdx.y, n = blockIdx.z;
     const int j0 = strip * TWO, i0 = seg * p.seg_rows;
     const int rows_out = min(p.seg_rows, p.Hout - i0);
@@ -132,16 +173,20 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
     const int chi = (strip == p.nstrip - 1) ? p.W : j0 + TWO + HALO / 2;
     constexpr float kVifEps = 1e-10f, kVifNoise = 325.125f;            // metric.py:407-408
 
+    const bool fast_terms = p.pixel_combine == MMIF_COMBINE_MAX && p.grad_combine == MMIF_COMBINE_MAX &&
+                            p.pixel_norm == MMIF_NORM_L1 && p.grad_norm == MMIF_NORM_L1;
     for (int b = 0; b < nb; ++b) {
         ring_wait(sm, src, b + 2);
-        if (b + 1 < nb) ring_issue(sm, src, &map1, &map2, &mapy, b + 3);
-        vpass_moments<WIN>(sm, p.taps, sh, (b & 3) * kRB);
+        vpass_moments<WIN>(sm, p.taps, sh, (b % 3) * kRB);
         if (EPI == EPI_SSIM && p.do_sobel) {
             const int rlo = (seg == 0 && b == 0) ? 0 : i0 + b * kRB + HALO / 2;
             const int rhi = (seg == p.nseg - 1 && b == nb - 1) ? p.H : i0 + b * kRB + kRB + HALO / 2;
-            fwd_sobel_pixel(sm, p, i0, j0, rlo, rhi, clo, chi, pix_sum, grad_sum);
+            if (fast_terms) fwd_sobel_pixel_fast(sm, p.H, p.W, i0, j0, rlo, rhi, clo, chi, pix_sum, grad_sum);
+            else fwd_sobel_pixel(sm, p, i0, j0, rlo, rhi, clo, chi, pix_sum, grad_sum);
         }
         __syncthreads();
+        // group b is dead now (V-pass and Sobel rows of batch b+1 start at group b+1): refill its slot
+        if (b + 1 < nb) ring_issue(sm, src, &map1, &map2, &mapy, b + 3);
         const int rows_b = min(kRB, rows_out - b * kRB);
         if (ho < rows_b && hg * 8 < cols_out) {
             float2 acc[8][4];

@@ -23,17 +23,31 @@ namespace mmif {
 constexpr int kNT = 128;        // threads per CTA
 constexpr int kTWI = 128;       // input columns per strip
 constexpr int kRB = 8;          // output rows per batch
-constexpr int kRingRows = 32;   // 4 slots x 8 rows
 constexpr int kVCols = 136;     // vbuf columns (128 + read-ahead pad)
 constexpr int kVPitch = 4 * kVCols + 2;   // float2 units per output row (pad 16 B -> pitch = 16 mod 128 B)
-constexpr int kGroupBytes = 3 * kRB * kTWI * 4;
 
-struct Smem {
-    float ring[3][kRingRows][kTWI];       // 49152 B
-    float2 vbuf[kRB * kVPitch];           // 34944 B
+// SLOTS 8-row groups of RP columns per image.  Forward: 3 slots x 128 (36 KB; the group for batch b+1
+// is fetched while batch b is in its H-pass) so that 3 CTAs fit an SM; backward: 4 slots x 132
+// (row pitch = 16 mod 128 B: its combine step reads 8 rows at a time with LDS.128, conflict-free).
+template <int SLOTS, int RP>
+struct SmemT {
+    static constexpr int kSlots = SLOTS;
+    static constexpr int kRows = SLOTS * kRB;
+    static constexpr int kPitch = RP;
+    static constexpr int kGroupBytes = 3 * kRB * RP * 4;
+    float ring[3][SLOTS * kRB][RP];
+    alignas(16) float2 vbuf[kRB * kVPitch];           // 34944 B
     unsigned long long mbar[4];
     double red[8 * (kNT / 32)];
     int flag;
+    __device__ __forceinline__ static int wrap(int r) {          // r in [0, 2*kRows)
+        if (SLOTS == 4) return r & (kRows - 1);
+        return r >= kRows ? r - kRows : r;
+    }
+    __device__ __forceinline__ static int wrap_any(int r) {      // any r >= 0
+        if (SLOTS == 4) return r & (kRows - 1);
+        return r % kRows;
+    }
 };
 
 // ---- input ring -------------------------------------------------------------------------
@@ -45,34 +59,38 @@ struct RingSrc {
     bool use_tma;
 };
 
-__device__ __forceinline__ void ring_issue(Smem& sm, const RingSrc& s, const CUtensorMap* m0, const CUtensorMap* m1,
+template <class SM>
+__device__ __forceinline__ void ring_issue(SM& sm, const RingSrc& s, const CUtensorMap* m0, const CUtensorMap* m1,
                                            const CUtensorMap* m2, int g) {
-    const int slot = g & 3;
+    const int slot = g % SM::kSlots;
     if (s.use_tma) {
         if (threadIdx.x == 0) {
             unsigned long long* bar = &sm.mbar[slot];
-            mbar_expect_tx((uint64_t*)bar, kGroupBytes);
+            mbar_expect_tx((uint64_t*)bar, SM::kGroupBytes);
             tma_load_3d(&sm.ring[0][slot * kRB][0], m0, s.col0, s.row0 + g * kRB, s.n, (uint64_t*)bar);
             tma_load_3d(&sm.ring[1][slot * kRB][0], m1, s.col0, s.row0 + g * kRB, s.n, (uint64_t*)bar);
             tma_load_3d(&sm.ring[2][slot * kRB][0], m2, s.col0, s.row0 + g * kRB, s.n, (uint64_t*)bar);
         }
     } else {
-        const int col = s.col0 + (int)threadIdx.x;
-        const bool cok = (col >= 0) && (col < s.W);
+        for (int tc = threadIdx.x; tc < SM::kPitch; tc += kNT) {
+            const int col = s.col0 + tc;
+            const bool cok = (col >= 0) && (col < s.W);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 3; ++k) {
 #pragma unroll
-            for (int r = 0; r < kRB; ++r) {
-                const int row = s.row0 + g * kRB + r;
-                float v = 0.f;
-                if (cok && row >= 0 && row < s.H) v = __ldg(s.img[k] + (size_t)row * s.W + col);
-                sm.ring[k][slot * kRB + r][threadIdx.x] = v;
+                for (int r = 0; r < kRB; ++r) {
+                    const int row = s.row0 + g * kRB + r;
+                    float v = 0.f;
+                    if (cok && row >= 0 && row < s.H) v = __ldg(s.img[k] + (size_t)row * s.W + col);
+                    sm.ring[k][slot * kRB + r][tc] = v;
+                }
             }
         }
     }
 }
-__device__ __forceinline__ void ring_wait(Smem& sm, const RingSrc& s, int g) {
-    if (s.use_tma) mbar_wait((uint64_t*)&sm.mbar[g & 3], (g >> 2) & 1);
+template <class SM>
+__device__ __forceinline__ void ring_wait(SM& sm, const RingSrc& s, int g) {
+    if (s.use_tma) mbar_wait((uint64_t*)&sm.mbar[g % SM::kSlots], (g / SM::kSlots) & 1);
 }
 
 // ---- mean shift + window-sum correction ---------------------------------------------------
@@ -142,18 +160,17 @@ __device__ __forceinline__ Stats stats_from(const Moments& m, const Shift& h) {
 
 // ---- V-pass: vertical WIN-tap blur of the four packed moment maps --------------------------
 // `base` = ring-local index of the first input row of this batch (multiple of 8).
-template <int WIN>
-__device__ __forceinline__ void vpass_moments(Smem& sm, const Taps& tp, const Shift& h, int base) {
+template <int WIN, class SM>
+__device__ __forceinline__ void vpass_moments(SM& sm, const Taps& tp, const Shift& h, int base) {
     const int t = threadIdx.x;
     float2 acc[kRB][4];
+    const float2 negc = f2(-h.c.x, -h.c.y);
 #pragma unroll
     for (int rr = 0; rr < kRB + WIN - 1; ++rr) {
-        const int lr = (base + rr) & (kRingRows - 1);
-        const float a = sm.ring[0][lr][t] - h.c.x;
-        const float b = sm.ring[1][lr][t] - h.c.y;
+        const int lr = SM::wrap(base + rr);
         const float y = sm.ring[2][lr][t] - h.cy;
         float2 P[4];
-        P[0] = f2(a, b);
+        P[0] = add2(f2(sm.ring[0][lr][t], sm.ring[1][lr][t]), negc);
         P[1] = mul2(P[0], P[0]);
         P[2] = muls(y, P[0]);
         P[3] = f2(y, y * y);
@@ -217,7 +234,8 @@ __device__ __forceinline__ Moments moments_of(const float2 (&a)[4]) {
 // rounding noise of the shifted moments (~1e-7 (v-c)^2) never exceeds that of the reference's
 // unshifted fp32 moments (~1e-7 v^2), dark flat regions (v == c) become exact, and the values of a
 // well-exposed tile shrink by its floor.  Must be called by all threads (one __syncthreads).
-__device__ __forceinline__ Shift tile_shift(Smem& sm, const float* x1, const float* x2, const float* y, int H, int W, int r0, int nr,
+template <class SM>
+__device__ __forceinline__ Shift tile_shift(SM& sm, const float* x1, const float* x2, const float* y, int H, int W, int r0, int nr,
                                             int c0, const Taps& tp) {
     const int t = threadIdx.x;
     int r = r0 + ((t >> 4) * nr) / 8 + nr / 16;
