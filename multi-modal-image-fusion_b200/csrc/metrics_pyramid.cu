@@ -81,37 +81,63 @@ static int run_ssim_level(const float* a, const float* b, const float* f, int N,
 
 // =============================================================================== pyramid steps
 // MS-SSIM level step (metric.py:389-395): reflect-pad the odd edge, 2x2 mean.  ATen's avg_pool2d
-// adds the window in row-major order and divides by 4.
+// adds the window in row-major order and divides by 4.  One output per thread; each thread reads
+// two float2 (coalesced 8-byte loads) when the row pitch allows.
 struct Ptr3 { const float* src[3]; float* dst[3]; };
 __global__ void __launch_bounds__(256) halve_kernel(Ptr3 p, int N, int H, int W, int Ho, int Wo) {
-    const int k = blockIdx.z;
-    const long long total = (long long)N * Ho * Wo;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int n = (int)(idx / ((long long)Ho * Wo));
-    const int rem = (int)(idx % ((long long)Ho * Wo));
-    const int i = rem / Wo, j = rem % Wo;
+    const int k = blockIdx.z % 3, n = blockIdx.z / 3;
+    const int j = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int i = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= Ho || j >= Wo) return;
     const float* s = p.src[k] + (size_t)n * H * W;
     const int r0 = 2 * i, r1 = (2 * i + 1 < H) ? 2 * i + 1 : H - 2;
     const int c0 = 2 * j, c1 = (2 * j + 1 < W) ? 2 * j + 1 : W - 2;
-    const float v = ((s[(size_t)r0 * W + c0] + s[(size_t)r0 * W + c1]) + s[(size_t)r1 * W + c0]) + s[(size_t)r1 * W + c1];
-    p.dst[k][idx] = v * 0.25f;
+    float a, b, c, d;
+    if ((W & 1) == 0 && (((uintptr_t)s) & 7) == 0) {
+        const float2 t0 = __ldg(reinterpret_cast<const float2*>(s + (size_t)r0 * W + c0));
+        const float2 t1 = __ldg(reinterpret_cast<const float2*>(s + (size_t)r1 * W + c0));
+        a = t0.x; b = t0.y; c = t1.x; d = t1.y;
+    } else {
+        a = __ldg(s + (size_t)r0 * W + c0); b = __ldg(s + (size_t)r0 * W + c1);
+        c = __ldg(s + (size_t)r1 * W + c0); d = __ldg(s + (size_t)r1 * W + c1);
+    }
+    p.dst[k][((size_t)n * Ho + i) * Wo + j] = (((a + b) + c) + d) * 0.25f;
 }
 
 // VIF scale step (metric.py:419-423): valid k x k Gaussian blur, then every other row / column.
+// Tile of 32 x 16 outputs per CTA: the (64+k-1) x (32+k-1) input patch is staged in shared memory,
+// blurred horizontally at the even columns, then vertically at the even rows (separable: 3k FMA per
+// output instead of k^2).
+constexpr int kBdTx = 32, kBdTy = 16, kBdMaxK = 9;
 __global__ void __launch_bounds__(256) blur_decimate_kernel(Ptr3 p, int N, int H, int W, int Ho, int Wo, int k, const Taps taps) {
-    const int im = blockIdx.z;
-    const long long total = (long long)N * Ho * Wo;
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int n = (int)(idx / ((long long)Ho * Wo));
-    const int rem = (int)(idx % ((long long)Ho * Wo));
-    const int i = rem / Wo, j = rem % Wo;
-    const float* s = p.src[im] + (size_t)n * H * W + (size_t)(2 * i) * W + 2 * j;
-    float acc = 0.f;
-    for (int u = 0; u < k; ++u)
-        for (int v = 0; v < k; ++v) acc = fmaf(taps.w[u] * taps.w[v], s[(size_t)u * W + v], acc);
-    p.dst[im][idx] = acc;
+    __shared__ float tin[2 * kBdTy + kBdMaxK - 1][2 * kBdTx + kBdMaxK - 1 + 1];
+    __shared__ float tmid[2 * kBdTy + kBdMaxK - 1][kBdTx + 1];
+    const int im = blockIdx.z % 3, n = blockIdx.z / 3;
+    const float* s = p.src[im] + (size_t)n * H * W;
+    const int oj0 = blockIdx.x * kBdTx, oi0 = blockIdx.y * kBdTy;
+    const int rows_in = 2 * kBdTy + k - 1, cols_in = 2 * kBdTx + k - 1;
+    const int r0 = 2 * oi0, c0 = 2 * oj0;
+    for (int idx = threadIdx.x; idx < rows_in * cols_in; idx += 256) {
+        const int r = idx / cols_in, c = idx % cols_in;
+        const int gr = r0 + r, gc = c0 + c;
+        tin[r][c] = (gr < H && gc < W) ? __ldg(s + (size_t)gr * W + gc) : 0.f;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows_in * kBdTx; idx += 256) {
+        const int r = idx / kBdTx, j = idx % kBdTx;
+        float acc = 0.f;
+        for (int v = 0; v < k; ++v) acc = fmaf(taps.w[v], tin[r][2 * j + v], acc);
+        tmid[r][j] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kBdTy * kBdTx; idx += 256) {
+        const int i = idx / kBdTx, j = idx % kBdTx;
+        if (oi0 + i < Ho && oj0 + j < Wo) {
+            float acc = 0.f;
+            for (int u = 0; u < k; ++u) acc = fmaf(taps.w[u], tmid[2 * i + u][j], acc);
+            p.dst[im][((size_t)n * Ho + oi0 + i) * Wo + oj0 + j] = acc;
+        }
+    }
 }
 
 // =============================================================================== compose kernels
@@ -286,7 +312,7 @@ static int run_msssim(const float* a, const float* b, const float* f, int N, int
         const size_t per = (size_t)N * ho * wo;
         p.src[0] = ca; p.src[1] = cb; p.src[2] = cf;
         p.dst[0] = base; p.dst[1] = base + per; p.dst[2] = base + 2 * per;
-        dim3 grid((unsigned)((per + 255) / 256), 1, 3);
+        dim3 grid(ceil_div(wo, 64), ceil_div(ho, 4), 3 * N);
         halve_kernel<<<grid, 256, 0, st>>>(p, N, d.h[l], d.w[l], ho, wo);
         MMIF_CUDA(cudaGetLastError());
         ca = p.dst[0]; cb = p.dst[1]; cf = p.dst[2];
@@ -311,7 +337,7 @@ static int run_vif(const float* a, const float* b, const float* f, int N, int H,
             const size_t per = (size_t)N * ho * wo;
             p.src[0] = ca; p.src[1] = cb; p.src[2] = cf;
             p.dst[0] = base; p.dst[1] = base + per; p.dst[2] = base + 2 * per;
-            dim3 grid((unsigned)((per + 255) / 256), 1, 3);
+            dim3 grid(ceil_div(wo, kBdTx), ceil_div(ho, kBdTy), 3 * N);
             blur_decimate_kernel<<<grid, 256, 0, st>>>(p, N, d.h[s - 1], d.w[s - 1], ho, wo, k, taps);
             MMIF_CUDA(cudaGetLastError());
             ca = p.dst[0]; cb = p.dst[1]; cf = p.dst[2];

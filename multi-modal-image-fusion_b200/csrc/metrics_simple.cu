@@ -28,6 +28,7 @@ stats_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const fl
 #pragma unroll
         for (int i = 0; i < kStatK; ++i) s[i] = 0.f;
         float ff = __ldg(f + (size_t)r0 * W + c);
+#pragma unroll 4
         for (int r = r0; r < r1; ++r) {
             const size_t p = (size_t)r * W + c;
             const float fa = __ldg(a + p), fb = __ldg(b + p);
@@ -98,44 +99,64 @@ __device__ __forceinline__ int hist_bin(float v) {
     return b > 255 ? 255 : b;
 }
 
-// grid (4*S, N): CTA (g, s) owns rows [64g, 64g+64) of both joint histograms (2 x 64 KB of shared
-// memory, ATOMS throughput is bin-count independent: 7.6 atomics/clk/SM measured) and scans pixel
-// split s of the pair; every pixel is scanned by 4 CTAs (the pair stays in L2), counted by one.
-__global__ void __launch_bounds__(256)
+// grid (8*S, N): CTA (joint j, range g, split s) owns rows [64g, 64g+64) of ONE joint histogram
+// (64 KB of shared memory -> 3 CTAs per SM; ATOMS throughput is bin-count independent: 7.6
+// atomics/clk/SM measured) and scans pixel split s of (source_j, f); every pixel is scanned by 8
+// CTAs (the pair stays in L2) and counted by two of them.  4 pixels per thread per step (float4).
+__device__ __forceinline__ void hist_count(uint32_t* jh, uint32_t* exs, uint32_t* exf, int g, bool fextra, float vs, float vf) {
+    const int bs = hist_bin(vs), bf = hist_bin(vf);
+    if (bs >= 0 && (bs >> 6) == g) {
+        if (bf >= 0) atomicAdd(&jh[(bs & 63) * 256 + bf], 1u);
+        else atomicAdd(&exs[bs], 1u);                       // source counted in its marginal only
+    }
+    if (fextra && bs < 0 && bf >= 0) atomicAdd(&exf[bf], 1u);   // f marginal is derived from joint_af
+}
+
+__global__ void __launch_bounds__(256, 3)
 hist_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ F, long long P, int S,
             uint32_t* counts, uint32_t* extra) {
-    extern __shared__ uint32_t sh[];            // [2][64*256]
-    uint32_t* ja = sh;
-    uint32_t* jb = sh + 64 * 256;
-    const int n = blockIdx.y, g = blockIdx.x & 3, s = blockIdx.x >> 2;
-    for (int i = threadIdx.x; i < 2 * 64 * 256; i += 256) sh[i] = 0u;
+    extern __shared__ uint32_t jh[];            // [64*256]
+    const int n = blockIdx.y, j = blockIdx.x & 1, g = (blockIdx.x >> 1) & 3, s = blockIdx.x >> 3;
+    for (int i = threadIdx.x; i < 64 * 256; i += 256) jh[i] = 0u;
     __syncthreads();
-    const float* a = A + (size_t)n * P; const float* b = Bm + (size_t)n * P; const float* f = F + (size_t)n * P;
+    const float* src = (j == 0 ? A : Bm) + (size_t)n * P;
+    const float* f = F + (size_t)n * P;
     uint32_t* ex = extra + (size_t)n * 768;     // [extra_a | extra_b | extra_f]
-    const long long p0 = P * s / S, p1 = P * (s + 1) / S;
-    for (long long p = p0 + threadIdx.x; p < p1; p += 256) {
-        const int ba = hist_bin(__ldg(a + p)), bb = hist_bin(__ldg(b + p)), bf = hist_bin(__ldg(f + p));
-        if (ba >= 0 && (ba >> 6) == g) {
-            if (bf >= 0) atomicAdd(&ja[(ba & 63) * 256 + bf], 1u);
-            else atomicAdd(&ex[ba], 1u);                    // a counted in its marginal only
+    uint32_t* exs = ex + j * 256;
+    uint32_t* exf = ex + 512;
+    const bool fextra = (j == 0) && (g == 0);
+    long long p0 = P * s / S, p1 = P * (s + 1) / S;
+    const bool vec = ((P & 3) == 0) && ((((uintptr_t)src | (uintptr_t)f) & 15) == 0);
+    if (vec) {
+        p0 &= ~3ll;
+        if (s + 1 < S) p1 &= ~3ll;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        const float4* f4 = reinterpret_cast<const float4*>(f);
+        const long long q0 = p0 >> 2, q1 = p1 >> 2;
+        long long q = q0 + threadIdx.x;
+        for (; q + 256 < q1; q += 512) {            // two independent float4 pairs in flight
+            const float4 a0 = __ldg(s4 + q), b0 = __ldg(f4 + q), a1 = __ldg(s4 + q + 256), b1 = __ldg(f4 + q + 256);
+            hist_count(jh, exs, exf, g, fextra, a0.x, b0.x); hist_count(jh, exs, exf, g, fextra, a0.y, b0.y);
+            hist_count(jh, exs, exf, g, fextra, a0.z, b0.z); hist_count(jh, exs, exf, g, fextra, a0.w, b0.w);
+            hist_count(jh, exs, exf, g, fextra, a1.x, b1.x); hist_count(jh, exs, exf, g, fextra, a1.y, b1.y);
+            hist_count(jh, exs, exf, g, fextra, a1.z, b1.z); hist_count(jh, exs, exf, g, fextra, a1.w, b1.w);
         }
-        if (bb >= 0 && (bb >> 6) == g) {
-            if (bf >= 0) atomicAdd(&jb[(bb & 63) * 256 + bf], 1u);
-            else atomicAdd(&ex[256 + bb], 1u);
+        for (; q < q1; q += 256) {
+            const float4 a0 = __ldg(s4 + q), b0 = __ldg(f4 + q);
+            hist_count(jh, exs, exf, g, fextra, a0.x, b0.x); hist_count(jh, exs, exf, g, fextra, a0.y, b0.y);
+            hist_count(jh, exs, exf, g, fextra, a0.z, b0.z); hist_count(jh, exs, exf, g, fextra, a0.w, b0.w);
         }
-        if (g == 0 && ba < 0 && bf >= 0) atomicAdd(&ex[512 + bf], 1u);   // f marginal is derived from joint_af
+    } else {
+        for (long long p = p0 + threadIdx.x; p < p1; p += 256) hist_count(jh, exs, exf, g, fextra, __ldg(src + p), __ldg(f + p));
     }
     __syncthreads();
-    uint32_t* cn = counts + (size_t)n * MMIF_HIST_WORDS;
-    uint32_t* dst_a = cn + 768 + g * 64 * 256;
-    uint32_t* dst_b = cn + 768 + 65536 + g * 64 * 256;
+    uint32_t* dst = counts + (size_t)n * MMIF_HIST_WORDS + 768 + (size_t)j * 65536 + g * 64 * 256;
     if (S == 1) {
-        for (int i = threadIdx.x; i < 64 * 256; i += 256) { dst_a[i] = ja[i]; dst_b[i] = jb[i]; }
+        for (int i = threadIdx.x; i < 64 * 256; i += 256) dst[i] = jh[i];
     } else {
         for (int i = threadIdx.x; i < 64 * 256; i += 256) {
-            const uint32_t va = ja[i], vb = jb[i];
-            if (va) atomicAdd(&dst_a[i], va);
-            if (vb) atomicAdd(&dst_b[i], vb);
+            const uint32_t v = jh[i];
+            if (v) atomicAdd(&dst[i], v);
         }
     }
 }
@@ -202,16 +223,16 @@ hist_finalize_kernel(uint32_t* counts, uint32_t* extra, long long P, double* ent
 int launch_hist(const float* a, const float* b, const float* f, int N, int H, int W, uint32_t* counts, double* ent,
                 long long estride, MetricWs& ws, cudaStream_t st) {
     const long long P = (long long)H * W;
-    int S = 148 / (4 * N);
+    int S = (3 * 148 + 8 * N - 1) / (8 * N);
     S = S < 1 ? 1 : (S > 16 ? 16 : S);
     if (P < 65536) S = 1;
     static bool attr_done = false;
     if (!attr_done) {
-        MMIF_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 4));
+        MMIF_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 256 * 4));
         attr_done = true;
     }
-    dim3 grid(4 * S, N);
-    hist_kernel<<<grid, 256, 2 * 64 * 256 * 4, st>>>(a, b, f, P, S, counts, ws.hist_extra);
+    dim3 grid(8 * S, N);
+    hist_kernel<<<grid, 256, 64 * 256 * 4, st>>>(a, b, f, P, S, counts, ws.hist_extra);
     MMIF_CUDA(cudaGetLastError());
     hist_finalize_kernel<<<N, 256, 0, st>>>(counts, ws.hist_extra, P, ent, estride);
     MMIF_CUDA(cudaGetLastError());
@@ -271,7 +292,7 @@ qabf_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const flo
                     const float Qg = __fdiv_rn(0.9994f, 1.f + expf(-15.f * (G - 0.5f)));   // metric.py:218,224
                     const float Qa = __fdiv_rn(0.9879f, 1.f + expf(-22.f * (Aa - 0.8f)));  // metric.py:219,225
                     Q[k] = Qg * Qa;
-                    w[k] = powf(g[k], Lexp);
+                    w[k] = (Lexp == 1.5f) ? g[k] * sqrtf(g[k]) : powf(g[k], Lexp);    // eval.py:45 uses L=1.5
                 }
                 const float gmax = fmaxf(g[0], g[1]);
                 const float lossw = (1.f - Q[0]) * w[0] + (1.f - Q[1]) * w[1];
