@@ -164,13 +164,25 @@ def main():
     red = torch.zeros(4, device=dev)
     st = L.stream_ptr(dev)
 
-    def fwd():
+    cfg_z = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
+    cfg_z.want_grad = 1
+    dU = torch.empty_like(f)
+
+    def fwd():        # two-kernel path, kernel 1: loss values only (12 B/px)
         L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg),
                                          out.data_ptr(), None, ws.data_ptr(), ws.numel(), st))
 
-    def bwd():
+    def bwd():        # two-kernel path, kernel 2: recomputing backward (16 B/px)
         L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg),
-                                         gout.data_ptr(), dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
+                                         gout.data_ptr(), None, dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    def zfwd():       # single-pass path (what the drop-in modules run): loss values + d(total)/dIf in ONE launch (16 B/px)
+        L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg_z),
+                                         out.data_ptr(), dU.data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    def zbwd():       # its backward: upstream gradients equal -> streaming rescale of dU (+ an early-exit launch)
+        L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg_z),
+                                         gout.data_ptr(), dU.data_ptr(), dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
 
     def reduce_scalars():
         if world > 1:           # the path's only collective: ONE 16-byte all-reduce (train.py:92-96 does four)
@@ -183,61 +195,71 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(first, second, steps):
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t_begin.record()
+        for k in range(steps):
+            ev[k][0].record(); first(); ev[k][1].record(); second(); ev[k][2].record()
+            reduce_scalars()
+        t_end.record()
+        sync_all()
+        ms_total = t_begin.elapsed_time(t_end)
+        ms_a = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+        ms_b = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+        tmax = torch.tensor([ms_total], device=dev)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        return tmax.item() / steps, ms_a, ms_b
+
     for _ in range(max(args.warmup, 3)):
-        fwd(); bwd(); reduce_scalars()
+        zfwd(); zbwd(); reduce_scalars()
     sync_all()
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    t_begin.record()
-    for k in range(args.steps):
-        ev[k][0].record(); fwd(); ev[k][1].record(); bwd(); ev[k][2].record()
-        reduce_scalars()
-    t_end.record()
-    sync_all()
+    ms_step, ms_z, ms_rescale = timed(zfwd, zbwd, args.steps)
     clocks = sampler.stop()
-    ms_total = t_begin.elapsed_time(t_end)
-    ms_fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    ms_bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    tmax = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = tmax.item() / args.steps
+    for _ in range(3):
+        fwd(); bwd()
+    ms_step2, ms_fwd, ms_bwd = timed(fwd, bwd, args.steps)
     total_mpix = GLOBAL_B * H * W / 1e6
     value = total_mpix / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (backward: 16 algorithmic bytes per pixel) -------------
+    # ---- roofline of the dominant kernel (single-pass loss+gradient: 16 algorithmic bytes per pixel) ----
     peak, peak_src = measured_peak()
     local_pix = B * H * W
-    ach_bwd = ALG_BYTES_BWD * local_pix / (ms_bwd * 1e-3) / 1e9
-    ach_fwd = ALG_BYTES_FWD * local_pix / (ms_fwd * 1e-3) / 1e9
+    gbs = lambda bpp, ms: bpp * local_pix / (ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             tj = json.load(fh)
-        traffic = tj['fusion_loss_bwd_kernel']['dram_bytes_per_pixel'] * local_pix
+        traffic = tj['fusion_loss_bwd_kernel<FAST,ZMODE>']['dram_bytes_per_pixel'] * local_pix
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_bwd_kernel', 'achieved': ach_bwd, 'peak': peak, 'unit': 'GB/s',
-                'frac': ach_bwd / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_pixel': ALG_BYTES_BWD, 'ms_per_launch': ms_bwd,
-                'note': 'fp32-issue bound, not HBM bound: see DESIGN.md (FMA pipe roof) and profiles/'}
-    roofline_fwd = {'bound': 'hbm', 'kernel': 'moment_fwd_kernel<11,EPI_SSIM>', 'achieved': ach_fwd, 'peak': peak, 'unit': 'GB/s',
-                    'frac': ach_fwd / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_FWD, 'ms_per_launch': ms_fwd}
+    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_bwd_kernel<FAST=1,ZMODE=1> (loss values + dIf, one launch)',
+                'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
+                'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
+                'ms_per_launch': ms_z,
+                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/): the pipe roof is ~58 Gpix/s'}
+    two_kernel = {'value': total_mpix / (ms_step2 * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step2,
+                  'fwd': {'kernel': 'moment_fwd_kernel<11,EPI_SSIM>', 'ms_per_launch': ms_fwd, 'achieved': gbs(ALG_BYTES_FWD, ms_fwd),
+                          'frac': gbs(ALG_BYTES_FWD, ms_fwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_FWD},
+                  'bwd': {'kernel': 'fusion_loss_bwd_kernel<FAST=1,ZMODE=0>', 'ms_per_launch': ms_bwd, 'achieved': gbs(ALG_BYTES_BWD, ms_bwd),
+                          'frac': gbs(ALG_BYTES_BWD, ms_bwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD},
+                  'combined_28B': {'achieved': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd),
+                                   'frac': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd) / peak}}
 
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'per_rank_batch': B, 'parallelism': f'batch sharded over {world} rank(s)',
+                   'path': 'single-pass (loss + gradient in one launch, streaming rescale in backward); two_kernel = fwd then recomputing bwd',
                    'l2': 'inputs larger than L2 (per-rank tensors %.0f MB each)' % (B * H * W * 4 / 1e6),
                    'collective': 'one 16-byte all-reduce of the loss scalars per step' if world > 1 else 'none'},
-        'roofline': roofline, 'roofline_fwd': roofline_fwd, 'clocks': clocks,
-        'gpu_launches': 2 * args.steps,
-        'combined_fwd_bwd': {'achieved': (ALG_BYTES_FWD + ALG_BYTES_BWD) * local_pix / ((ms_fwd + ms_bwd) * 1e-3) / 1e9,
-                             'unit': 'GB/s', 'frac': (ALG_BYTES_FWD + ALG_BYTES_BWD) * local_pix / ((ms_fwd + ms_bwd) * 1e-3) / 1e9 / peak},
+        'roofline': roofline, 'rescale_ms': ms_rescale, 'two_kernel': two_kernel, 'clocks': clocks,
+        'gpu_launches': 3 * args.steps,
     }
 
     if not args.no_extras:

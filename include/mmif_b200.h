@@ -58,8 +58,9 @@ typedef struct MmifLossCfg {
     int32_t grad_combine;  /* MMIF_COMBINE_*  */
     int32_t pixel_norm;    /* MMIF_NORM_*     */
     int32_t grad_norm;     /* MMIF_NORM_*     */
-    int32_t want_grad;     /* fwd only: !=0 -> also write d(total)/d(imgf) for unit upstream
-                              gradients into `dF_unit` (single-pass variant), else ignored */
+    int32_t want_grad;     /* fwd only: !=0 -> single-pass variant: the same launch also writes
+                              d(l_ssim + l_pixel + l_grad)/d(imgf) (unit upstream gradients, the
+                              weights above applied) into `dF_unit`; else ignored */
     int32_t reserved;
 } MmifLossCfg;
 
@@ -96,10 +97,13 @@ int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B
                          void* ws, size_t ws_bytes, void* stream);
 
 /* Replaces autograd's backward of the three modules w.r.t. imgf (train.py:71): recomputes the
- * stencil and writes dF = g[0]*dLssim/dIf + g[1]*dLpixel/dIf + g[2]*dLgrad/dIf.
- * gout3: 3 floats in DEVICE memory (upstream gradients of the three loss values). */
+ * stencil and writes dF = g[0]*w_ssim*dLssim/dIf + g[1]*w_pixel*dLpixel/dIf + g[2]*w_grad*dLgrad/dIf.
+ * gout3: 3 floats in DEVICE memory (upstream gradients of the three loss values).
+ * dF_unit: NULL, or the buffer a want_grad forward (same inputs, same cfg) filled.  When it is given
+ * and the three upstream gradients are equal (total = l1 + l2 + l3, train.py:69) the kernel only
+ * rescales it (8 B/pixel); otherwise it recomputes.  The decision is taken on the device. */
 int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
-                         const MmifLossCfg* cfg, const float* gout3, float* dF,
+                         const MmifLossCfg* cfg, const float* gout3, const float* dF_unit, float* dF,
                          void* ws, size_t ws_bytes, void* stream);
 
 /* TVLoss.forward (loss.py:347-358) on x [N][H][W]: out[0] = w*(norm(dv) + norm(dh)). */

@@ -57,7 +57,7 @@ def load():
     lib.mmif_loss_out_doubles.restype = sz
     lib.mmif_loss_out_doubles.argtypes = [ci]
     lib.mmif_fusion_loss_fwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, sz, vp]
-    lib.mmif_fusion_loss_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, sz, vp]
+    lib.mmif_fusion_loss_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, sz, vp]
     lib.mmif_tv_loss.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_metric_workspace_bytes.restype = sz
     lib.mmif_metric_workspace_bytes.argtypes = [ci, ci, ci]

@@ -23,9 +23,9 @@ __all__ = ['SSIM', 'MS_SSIM', 'MSW_SSIM', 'SSIMLoss', 'PixelLoss', 'GradLoss', '
 eps = 1e-7
 
 
-def _cfg(data_range, pixel_combine, grad_combine, pixel_norm, grad_norm):
+def _cfg(data_range, pixel_combine, grad_combine, pixel_norm, grad_norm, w_ssim=1.0, w_pixel=1.0, w_grad=1.0):
     c = L.MmifLossCfg()
-    c.w_ssim = c.w_pixel = c.w_grad = 1.0     # weights are applied by the modules (autograd scales)
+    c.w_ssim, c.w_pixel, c.w_grad = float(w_ssim), float(w_pixel), float(w_grad)
     c.data_range = float(data_range)
     c.pixel_combine, c.grad_combine = L.COMBINE[pixel_combine], L.COMBINE[grad_combine]
     c.pixel_norm, c.grad_norm = L.NORM[pixel_norm], L.NORM[grad_norm]
@@ -33,7 +33,11 @@ def _cfg(data_range, pixel_combine, grad_combine, pixel_norm, grad_norm):
 
 
 class _FusedObjective(torch.autograd.Function):
-    """(img1, img2, imgf) -> (1 - mean ssim, pixel norm, grad norm, per-sample ssim dict block)."""
+    """(img1, img2, imgf) -> (w1 (1 - mean ssim), w2 pixel norm, w3 grad norm, per-sample ssim dict block).
+
+    When imgf needs a gradient the forward runs the single-pass kernel (loss values AND
+    d(l1+l2+l3)/d imgf in one launch); backward then only rescales that buffer if the three upstream
+    gradients are equal — decided on the device, so there is no host sync — and recomputes otherwise."""
 
     @staticmethod
     def forward(ctx, img1, img2, imgf, cfg_key):
@@ -46,6 +50,9 @@ class _FusedObjective(torch.autograd.Function):
         dev = y.device
         L.ensure_device(dev)
         cfg = _cfg(*cfg_key)
+        want_grad = bool(imgf.requires_grad and torch.is_grad_enabled() and SINGLE_PASS)
+        cfg.want_grad = 1 if want_grad else 0
+        dF_unit = torch.empty_like(y) if want_grad else None
         out = torch.empty(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device=dev)
         nws = lib.mmif_loss_workspace_bytes(B, H, W)
         if nws == 0:
@@ -53,8 +60,10 @@ class _FusedObjective(torch.autograd.Function):
         ws = L.workspace(dev, nws, 'loss', (B, H, W))
         with torch.cuda.device(dev):
             L.check(lib.mmif_fusion_loss_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),
-                                             out.data_ptr(), None, ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+                                             out.data_ptr(), dF_unit.data_ptr() if want_grad else None,
+                                             ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
         ctx.save_for_backward(x1, x2, y)
+        ctx.dF_unit = dF_unit
         ctx.cfg_key, ctx.dims, ctx.in_shape = cfg_key, (B, H, W), imgf.shape
         vals = out[:3].to(torch.float32)
         per_sample = out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE).to(torch.float32)
@@ -71,11 +80,16 @@ class _FusedObjective(torch.autograd.Function):
         g = torch.stack([zero if t is None else t.to(torch.float32).reshape(()) for t in (g_ssim, g_pix, g_grad)])
         dF = torch.empty_like(y)
         cfg = _cfg(*ctx.cfg_key)
+        unit = ctx.dF_unit
         ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
         with torch.cuda.device(dev):
             L.check(lib.mmif_fusion_loss_bwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),
-                                             g.data_ptr(), dF.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+                                             g.data_ptr(), unit.data_ptr() if unit is not None else None, dF.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
         return None, None, dF.view(ctx.in_shape), None
+
+
+SINGLE_PASS = True   # set False to force the two-kernel (forward, then recomputing backward) path
 
 
 class _Memo:
@@ -83,12 +97,13 @@ class _Memo:
 
     def __init__(self):
         self.key, self.refs, self.value = None, None, None
-        # modes the sibling modules asked for last time: the guess for the next fused launch
-        self.hint = {'pixel': ('max', 'l1'), 'grad': ('max', 'l1'), 'data_range': 1.0}
+        # what the sibling modules asked for last time: the guess for the next fused launch
+        self.hint = {'pixel': ('max', 'l1'), 'grad': ('max', 'l1'), 'data_range': 1.0,
+                     'w_ssim': 1.0, 'w_pixel': 0.01, 'w_grad': 0.1}
 
     def lookup(self, img1, img2, imgf, cfg_key):
         key = (img1.data_ptr(), img1._version, img2.data_ptr(), img2._version, imgf.data_ptr(), imgf._version,
-               tuple(imgf.shape), imgf.device, cfg_key, imgf.requires_grad and torch.is_grad_enabled())
+               tuple(imgf.shape), imgf.device, cfg_key, imgf.requires_grad and torch.is_grad_enabled(), SINGLE_PASS)
         if self.key == key and all(r() is t for r, t in zip(self.refs, (img1, img2, imgf))):
             return self.value
         if img1.requires_grad or img2.requires_grad:
@@ -102,17 +117,15 @@ class _Memo:
 _memo = _Memo()
 
 
-def _fused(img1, img2, imgf, data_range=None, pixel=None, grad=None):
+def _fused(img1, img2, imgf, data_range=None, pixel=None, grad=None, w_ssim=None, w_pixel=None, w_grad=None):
     for t, nm in ((img1, 'img1'), (img2, 'img2'), (imgf, 'imgf')):
         L.require_cuda(t, nm)
     h = _memo.hint
-    if data_range is not None:
-        h['data_range'] = float(data_range)
-    if pixel is not None:
-        h['pixel'] = pixel
-    if grad is not None:
-        h['grad'] = grad
-    cfg_key = (h['data_range'], h['pixel'][0], h['grad'][0], h['pixel'][1], h['grad'][1])
+    for k, v in (('data_range', data_range), ('pixel', pixel), ('grad', grad), ('w_ssim', w_ssim), ('w_pixel', w_pixel),
+                 ('w_grad', w_grad)):
+        if v is not None:
+            h[k] = float(v) if not isinstance(v, tuple) else v
+    cfg_key = (h['data_range'], h['pixel'][0], h['grad'][0], h['pixel'][1], h['grad'][1], h['w_ssim'], h['w_pixel'], h['w_grad'])
     return _memo.lookup(img1, img2, imgf, cfg_key)
 
 
@@ -198,8 +211,8 @@ class SSIMLoss(nn.Module):
         if self.mode == 'ssim':
             if self.use_padding:
                 raise NotImplementedError('use_padding=True is not built yet')
-            one_minus, _, _, _ = _fused(img1, img2, imgf, data_range=self.data_range)
-            return self.weight * one_minus
+            loss, _, _, _ = _fused(img1, img2, imgf, data_range=self.data_range, w_ssim=self.weight)
+            return loss
         elif self.mode == 'w-ssim':
             if self.use_padding:
                 raise NotImplementedError('use_padding=True is not built yet')
@@ -228,8 +241,8 @@ class PixelLoss(nn.Module):
         if mode not in ('avg', 'max'):
             return None  # the reference falls through and returns None (loss.py:294-304)
         _check_norm(self.mode)
-        _, pix, _, _ = _fused(img1, img2, imgf, pixel=(mode, self.mode))
-        return self.weight * pix
+        _, pix, _, _ = _fused(img1, img2, imgf, pixel=(mode, self.mode), w_pixel=self.weight)
+        return pix
 
 
 class GradLoss(nn.Module):
@@ -247,8 +260,8 @@ class GradLoss(nn.Module):
         if mode not in ('avg', 'max'):
             return None
         _check_norm(self.mode)
-        _, _, grd, _ = _fused(img1, img2, imgf, grad=(mode, self.mode))
-        return self.weight * grd
+        _, _, grd, _ = _fused(img1, img2, imgf, grad=(mode, self.mode), w_grad=self.weight)
+        return grd
 
 
 class TVLoss(nn.Module):

@@ -41,6 +41,9 @@ struct BwdParams {
     float w_ssim, w_pixel, w_grad;
     int use_tma;
     int vec_store;
+    const float* dF_unit;    // != nullptr: gradient already computed for unit upstream (single-pass forward);
+                             // if the three upstream gradients are equal the kernel only rescales it
+    FinishParams fin;        // ZMODE: loss sums / finish (same protocol as the forward kernel)
 };
 
 constexpr int kCPitch = 2 * kTWI + 2;   // float2 units per coefficient row (2 pair-maps x 128 + 16 B pad)
@@ -60,7 +63,11 @@ struct SmemBwd {
     alignas(16) float gbuf[kRB][kTMC + 4];   // pixel + Sobel gradient of the batch rows (row pitch 464 B = 80 mod 128)
 };
 
-template <bool FAST>      // FAST: mode='max' + 'l1' for both terms (train.py:67-68,307-308), no run-time mode switches
+// FAST : mode='max' + 'l1' for both terms (train.py:67-68,307-308), no run-time mode switches.
+// ZMODE: single-pass variant — the same launch also accumulates the three loss values (every window
+//        position / pixel is owned by exactly one CTA: the one whose gradient tile contains it), so
+//        forward + backward cost one kernel and 16 B/pixel instead of two kernels and 28 B/pixel.
+template <bool FAST, bool ZMODE>
 __global__ void __launch_bounds__(kNT, 2)
 fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
@@ -88,7 +95,14 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
     __syncthreads();
     const Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, R0, iend - R0 + HALO, jw0, p.taps);
-    const float g_ssim = __ldg(p.gout + 0), g_pix = __ldg(p.gout + 1), g_grad = __ldg(p.gout + 2);
+    const float g_ssim = p.gout ? __ldg(p.gout + 0) : 1.f, g_pix = p.gout ? __ldg(p.gout + 1) : 1.f,
+                g_grad = p.gout ? __ldg(p.gout + 2) : 1.f;
+    if (!ZMODE && p.dF_unit != nullptr && g_ssim == g_pix && g_pix == g_grad) {
+        // total = l1 + l2 + l3 (train.py:69): the upstream gradients are one common scalar, and the
+        // single-pass forward already produced d(total)/dIf for unit upstream: rescale_unit_kernel
+        // (launched just before this kernel) has rescaled it, nothing to recompute.
+        return;
+    }
     const float npx = (float)p.B * (float)p.H * (float)p.W;
     const float k_ssim = g_ssim * p.w_ssim * (-0.5f) / ((float)p.B * (float)p.Hout * (float)p.Wout);
     const float k_pix = g_pix * p.w_pixel / npx * (p.pixel_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
@@ -120,6 +134,8 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     float2 s_dA = f2(0.f, 0.f), s_dB = s_dA, s_sA = s_dA, s_sB = s_dA, s_ucA = s_dA, s_ucB = s_dA;
     float s_dAy = 0.f, s_dBy = 0.f, s_sAy = 0.f, s_sBy = 0.f, s_ucAy = 0.f, s_ucBy = 0.f;
     float s_hxA = 0.f, s_hxB = 0.f, s_vyA = 0.f, s_vyB = 0.f;
+    float2 z_ss = f2(0.f, 0.f), z_cs = z_ss, z_sg = z_ss;     // ZMODE loss accumulators
+    float z_pix = 0.f, z_grad = 0.f;
 
     for (int b = 0; b < nb; ++b) {
         const int Rb = R0 + b * kRB;                  // first gradient row of this batch
@@ -158,6 +174,10 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                     else r = k_grad * (norm_der(Sy - S1, p.grad_norm) + norm_der(Sy - S2, p.grad_norm));
                     tx = mulsign(r, gxy);
                     ty = mulsign(r, gyy);
+                    if (ZMODE && s_own && qt >= i0 && qt < iend) {
+                        if (FAST || p.grad_combine == MMIF_COMBINE_MAX) z_grad += norm_val(Sy - fmaxf(S1, S2), FAST ? MMIF_NORM_L1 : p.grad_norm);
+                        else z_grad += 0.5f * (norm_val(Sy - S1, p.grad_norm) + norm_val(Sy - S2, p.grad_norm));
+                    }
                 }
                 const float txl = __shfl_up_sync(0xffffffffu, tx, 1), txr = __shfl_down_sync(0xffffffffu, tx, 1);
                 const float tyl = __shfl_up_sync(0xffffffffu, ty, 1), tyr = __shfl_down_sync(0xffffffffu, ty, 1);
@@ -171,7 +191,13 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                 if (FAST) G += mulsign(k_pix, s_ucAy - fmaxf(s_ucA.x, s_ucA.y));
                 else if (p.pixel_combine == MMIF_COMBINE_MAX) G += k_pix * norm_der(s_ucAy - fmaxf(s_ucA.x, s_ucA.y), p.pixel_norm);
                 else G += k_pix * (norm_der(s_ucAy - s_ucA.x, p.pixel_norm) + norm_der(s_ucAy - s_ucA.y, p.pixel_norm));
-                if (s_own && gi >= i0 && gi < iend) sb.gbuf[step][s_ci] = G;
+                if (s_own && gi >= i0 && gi < iend) {
+                    sb.gbuf[step][s_ci] = G;
+                    if (ZMODE) {
+                        if (FAST || p.pixel_combine == MMIF_COMBINE_MAX) z_pix += norm_val(s_ucAy - fmaxf(s_ucA.x, s_ucA.y), FAST ? MMIF_NORM_L1 : p.pixel_norm);
+                        else z_pix += 0.5f * (norm_val(s_ucAy - s_ucA.x, p.pixel_norm) + norm_val(s_ucAy - s_ucA.y, p.pixel_norm));
+                    }
+                }
                 s_dA = s_dB; s_dB = d; s_sA = s_sB; s_sB = sv; s_dAy = s_dBy; s_dBy = dy; s_sAy = s_sBy; s_sBy = sy;
                 s_hxA = s_hxB; s_hxB = hx; s_vyA = s_vyB; s_vyB = vy;
                 s_ucA = s_ucB; s_ucB = uc; s_ucAy = s_ucBy; s_ucBy = ucy;
@@ -216,6 +242,11 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                                               fma2(muls(-1.f, dvar), bcast(2.f * mo.my + sh.k1y), dmu));
                         ab[j] = f2(a.x + a.y, dvar.x + dvar.y);
                         cc[j] = dcov;
+                        if (ZMODE && q >= i0 && q < iend && pc >= j0 && pc < jend) {
+                            z_ss = add2(z_ss, S);
+                            z_cs = add2(z_cs, mul2(A2, rB2));
+                            z_sg = add2(z_sg, max2(vk, 1e-4f));
+                        }
                     }
                 }
             } else {
@@ -305,6 +336,40 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         }
         __syncthreads();
     }
+    if (ZMODE) {
+        double v[8] = {(double)z_ss.x, (double)z_ss.y, (double)z_cs.x, (double)z_cs.y, (double)z_sg.x, (double)z_sg.y,
+                       (double)z_pix, (double)z_grad};
+        cta_finish<kNT>(p.fin, v, sm.red, &sm.flag, n, seg * p.nstrip + strip, p.nstrip * p.nseg);
+    }
+}
+
+// Companion of the early exit above: dF = g * dF_unit when the three upstream gradients are equal,
+// nothing otherwise (the recomputing kernel then does the work).  Pure streaming, 8 B/pixel.
+__global__ void __launch_bounds__(256)
+rescale_unit_kernel(const float* __restrict__ gout, const float* __restrict__ unit, float* __restrict__ dF, size_t n, int vec) {
+    const float g0 = __ldg(gout + 0), g1 = __ldg(gout + 1), g2 = __ldg(gout + 2);
+    if (!(g0 == g1 && g1 == g2)) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const float4* u4 = reinterpret_cast<const float4*>(unit);
+        float4* d4 = reinterpret_cast<float4*>(dF);
+        const size_t n4 = n >> 2;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldcs(u4 + i + k * stride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) __stcs(d4 + i + k * stride, make_float4(g0 * v[k].x, g0 * v[k].y, g0 * v[k].z, g0 * v[k].w));
+        }
+        for (; i < n4; i += stride) {
+            const float4 v = __ldcs(u4 + i);
+            __stcs(d4 + i, make_float4(g0 * v.x, g0 * v.y, g0 * v.z, g0 * v.w));
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dF[(n4 << 2) + threadIdx.x] = g0 * unit[(n4 << 2) + threadIdx.x];
+    } else {
+        for (; i < n; i += stride) dF[i] = g0 * __ldg(unit + i);
+    }
 }
 
 // =============================================================================== host side
@@ -329,45 +394,27 @@ static int check_cfg(const MmifLossCfg* cfg) {
 
 using namespace mmif;
 
-// workspace = [fwd counters + partials][B x 8 per-sample sums]
-extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
+// workspace = [counters + partials (max of the forward / backward grids)][B x 8 per-sample sums]
+static size_t loss_ws_core_bytes(int B, int H, int W) {
     const size_t f = fwd_ws_bytes(WIN, B, H, W);
+    if (!f) return 0;
+    const BwdGeom g = bwd_geom(B, H, W);
+    const size_t z = ws_counters_bytes(B) + (size_t)B * g.nstrip * g.nseg * 8 * sizeof(double);
+    return f > z ? f : z;
+}
+extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
+    const size_t f = loss_ws_core_bytes(B, H, W);
     return f ? f + (size_t)B * 8 * sizeof(double) : 0;
 }
 extern "C" size_t mmif_loss_out_doubles(int B) { return (size_t)MMIF_LOSS_HEAD + (size_t)(B > 0 ? B : 0) * MMIF_LOSS_PER_SAMPLE; }
 
-extern "C" int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
-                                    const MmifLossCfg* cfg, double* out, float* dF_unit, void* ws, size_t ws_bytes,
-                                    void* stream) {
-    int rc = check_common(i1, i2, f, B, H, W);
-    if (rc) return rc;
-    rc = check_cfg(cfg);
-    if (rc) return rc;
-    if (!out) { set_error("null out"); return MMIF_E_NULL; }
-    if (cfg->want_grad || dF_unit) { set_error("single-pass gradient (want_grad) is not built yet"); return MMIF_E_MODE; }
-    const size_t fws = fwd_ws_bytes(WIN, B, H, W);
-    if (!ws || ws_bytes < mmif_loss_workspace_bytes(B, H, W)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
-    FwdLaunch L;
-    L.win = WIN; L.sigma = 1.5; L.epi = EPI_SSIM; L.finalize = FIN_LOSS; L.do_sobel = 1;
-    L.data_range = cfg->data_range; L.cfg = *cfg;
-    double* sums = (double*)((unsigned char*)ws + fws);
-    return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, out, ws, fws, (cudaStream_t)stream);
-}
-
-extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
-                                    const MmifLossCfg* cfg, const float* gout3, float* dF, void* ws, size_t ws_bytes,
-                                    void* stream) {
-    (void)ws; (void)ws_bytes;
-    int rc = check_common(i1, i2, f, B, H, W);
-    if (rc) return rc;
-    rc = check_cfg(cfg);
-    if (rc) return rc;
-    if (!gout3 || !dF) { set_error("null gout3/dF"); return MMIF_E_NULL; }
-    if (((uintptr_t)dF) & 3) { set_error("dF must be 4-byte aligned"); return MMIF_E_ALIGN; }
+static int launch_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, const MmifLossCfg* cfg,
+                      const float* gout3, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
     const BwdGeom g = bwd_geom(B, H, W);
     BwdParams p;
     memset(&p, 0, sizeof(p));
-    p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.gout = gout3;
+    p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.gout = gout3; p.dF_unit = dF_unit;
     p.B = B; p.H = H; p.W = W; p.Hout = g.Hout; p.Wout = g.Wout;
     p.seg_rows = g.seg_rows; p.nseg = g.nseg; p.nstrip = g.nstrip;
     make_taps(&p.taps, WIN, 1.5);
@@ -377,21 +424,82 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     p.pixel_norm = cfg->pixel_norm; p.grad_norm = cfg->grad_norm;
     p.w_ssim = cfg->w_ssim; p.w_pixel = cfg->w_pixel; p.w_grad = cfg->w_grad;
     p.vec_store = ((W & 3) == 0) && ((((uintptr_t)dF) & 15) == 0);
+    if (zmode) {
+        const size_t core = loss_ws_core_bytes(B, H, W);
+        if (!ws || ws_bytes < core + (size_t)B * 8 * sizeof(double)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
+        unsigned char* w8 = (unsigned char*)ws;
+        p.fin.B = B; p.fin.H = H; p.fin.W = W; p.fin.Hout = g.Hout; p.fin.Wout = g.Wout;
+        p.fin.finalize = FIN_LOSS;
+        p.fin.w_ssim = cfg->w_ssim; p.fin.w_pixel = cfg->w_pixel; p.fin.w_grad = cfg->w_grad;
+        p.fin.counters = (unsigned*)w8;
+        p.fin.partial = (double*)(w8 + ws_counters_bytes(B));
+        p.fin.sums = (double*)(w8 + core); p.fin.sums_stride = 8; p.fin.out = out;
+    }
     CUtensorMap m1, m2, my;
     p.use_tma = make_tensor_map(&m1, i1, B, H, W, kRPB, kRB) && make_tensor_map(&m2, i2, B, H, W, kRPB, kRB) &&
                 make_tensor_map(&my, f, B, H, W, kRPB, kRB);
     if (!p.use_tma) { memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2)); memset(&my, 0, sizeof(my)); }
     static bool attr_done = false;
     if (!attr_done) {
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd)));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemBwd)));
+        const int sz = (int)sizeof(SmemBwd);
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
         attr_done = true;
     }
     dim3 grid(g.nstrip, g.nseg, B);
+    if (!zmode && dF_unit) {
+        const size_t n = (size_t)B * H * W;
+        const int vec = (((uintptr_t)dF | (uintptr_t)dF_unit) & 15) == 0;
+        rescale_unit_kernel<<<148 * 8, 256, 0, st>>>(gout3, dF_unit, dF, n, vec);
+        MMIF_CUDA(cudaGetLastError());
+    }
     const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
                       cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
-    if (fast) fusion_loss_bwd_kernel<true><<<grid, kNT, sizeof(SmemBwd), (cudaStream_t)stream>>>(m1, m2, my, p);
-    else fusion_loss_bwd_kernel<false><<<grid, kNT, sizeof(SmemBwd), (cudaStream_t)stream>>>(m1, m2, my, p);
+    const size_t sm = sizeof(SmemBwd);
+    if (zmode) {
+        if (fast) fusion_loss_bwd_kernel<true, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        else fusion_loss_bwd_kernel<false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+    } else {
+        if (fast) fusion_loss_bwd_kernel<true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        else fusion_loss_bwd_kernel<false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+    }
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
+}
+
+extern "C" int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
+                                    const MmifLossCfg* cfg, double* out, float* dF_unit, void* ws, size_t ws_bytes,
+                                    void* stream) {
+    int rc = check_common(i1, i2, f, B, H, W);
+    if (rc) return rc;
+    rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!out) { set_error("null out"); return MMIF_E_NULL; }
+    if (!ws || ws_bytes < mmif_loss_workspace_bytes(B, H, W)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
+    if (cfg->want_grad) {
+        if (!dF_unit) { set_error("want_grad needs dF_unit"); return MMIF_E_NULL; }
+        if (((uintptr_t)dF_unit) & 3) { set_error("dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
+        return launch_bwd(i1, i2, f, B, H, W, cfg, nullptr, nullptr, dF_unit, true, out, ws, ws_bytes, (cudaStream_t)stream);
+    }
+    const size_t core = loss_ws_core_bytes(B, H, W);
+    FwdLaunch L;
+    L.win = WIN; L.sigma = 1.5; L.epi = EPI_SSIM; L.finalize = FIN_LOSS; L.do_sobel = 1;
+    L.data_range = cfg->data_range; L.cfg = *cfg;
+    double* sums = (double*)((unsigned char*)ws + core);
+    return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, out, ws, core, (cudaStream_t)stream);
+}
+
+extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
+                                    const MmifLossCfg* cfg, const float* gout3, const float* dF_unit, float* dF, void* ws,
+                                    size_t ws_bytes, void* stream) {
+    int rc = check_common(i1, i2, f, B, H, W);
+    if (rc) return rc;
+    rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!gout3 || !dF) { set_error("null gout3/dF"); return MMIF_E_NULL; }
+    if ((((uintptr_t)dF) | ((uintptr_t)dF_unit)) & 3) { set_error("dF / dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
+    if (dF_unit == dF) { set_error("dF must not alias dF_unit"); return MMIF_E_MODE; }
+    return launch_bwd(i1, i2, f, B, H, W, cfg, gout3, dF_unit, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -59,11 +59,14 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
     p.pixel_combine = L.cfg.pixel_combine; p.grad_combine = L.cfg.grad_combine;
     p.pixel_norm = L.cfg.pixel_norm; p.grad_norm = L.cfg.grad_norm;
     p.w_ssim = L.cfg.w_ssim; p.w_pixel = L.cfg.w_pixel; p.w_grad = L.cfg.w_grad;
-    p.do_sobel = L.do_sobel; p.finalize = L.finalize;
+    p.do_sobel = L.do_sobel;
     unsigned char* w8 = (unsigned char*)ws;
-    p.counters = (unsigned*)w8;
-    p.partial = (double*)(w8 + ws_counters_bytes(B));
-    p.sums = sums; p.sums_stride = sums_stride; p.out = out;
+    p.fin.B = B; p.fin.H = H; p.fin.W = W; p.fin.Hout = g.Hout; p.fin.Wout = g.Wout;
+    p.fin.finalize = L.finalize;
+    p.fin.w_ssim = L.cfg.w_ssim; p.fin.w_pixel = L.cfg.w_pixel; p.fin.w_grad = L.cfg.w_grad;
+    p.fin.counters = (unsigned*)w8;
+    p.fin.partial = (double*)(w8 + ws_counters_bytes(B));
+    p.fin.sums = sums; p.fin.sums_stride = sums_stride; p.fin.out = out;
     CUtensorMap m1, m2, my;
     p.use_tma = make_tensor_map(&m1, x1, B, H, W, kTWI, kRB) && make_tensor_map(&m2, x2, B, H, W, kTWI, kRB) &&
                 make_tensor_map(&my, y, B, H, W, kTWI, kRB);

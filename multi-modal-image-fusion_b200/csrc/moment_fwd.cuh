@@ -23,8 +23,83 @@ struct FwdGeo {
     static constexpr int TWO = ((kTWI - HALO) / 4) * 4;   // output columns per strip
 };
 
+// Everything the "last CTA finishes" logic needs; shared by the forward kernel and by the
+// single-pass (loss + gradient) mode of the backward kernel.
+struct FinishParams {
+    int B, H, W, Hout, Wout;
+    int finalize;            // FIN_SUMS / FIN_LOSS
+    float w_ssim, w_pixel, w_grad;
+    unsigned* counters;      // [B+1], zero on entry, left zero
+    double* partial;         // [B][nblk][8]
+    double* sums;            // per-sample raw sums: sums[n*sums_stride + 0..7]
+    long long sums_stride;
+    double* out;             // FIN_LOSS: loss block (mmif_b200.h MMIF_LOSS_*)
+};
+
+#ifdef __CUDACC__
+// v[] = this thread's 8 partial sums ([ssim1, ssim2, cs1, cs2, sig1, sig2, pix, grad] for the SSIM
+// epilogue).  Block-reduce, publish, and let the last CTA of sample n re-reduce that sample in a fixed
+// order; with FIN_LOSS the last sample-finisher writes the loss scalars.  All threads must call it.
+template <int NTHREADS>
+__device__ __forceinline__ void cta_finish(const FinishParams& p, double (&v)[8], double* red, int* flag, int n, int blk, int nblk) {
+    block_sum<8, NTHREADS>(v, red);
+    if (threadIdx.x == 0) {
+        double* dst = p.partial + ((size_t)n * nblk + blk) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = v[i];
+        __threadfence();
+        const unsigned prev = atomicAdd(&p.counters[n], 1u);
+        *flag = (prev == (unsigned)(nblk - 1));
+    }
+    __syncthreads();
+    if (!*flag) return;
+    __threadfence();
+    double t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = 0.0;
+    for (int k = threadIdx.x; k < nblk; k += NTHREADS) {
+        const double* srcp = p.partial + ((size_t)n * nblk + k) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] += __ldcg(srcp + i);
+    }
+    block_sum<8, NTHREADS>(t, red);
+    if (threadIdx.x == 0) {
+        double* sums = p.sums + (size_t)n * p.sums_stride;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sums[i] = t[i];
+        p.counters[n] = 0u;
+        if (p.finalize == FIN_LOSS) {
+            const double inv = 1.0 / ((double)p.Hout * (double)p.Wout);
+            double* so = p.out + MMIF_LOSS_HEAD + (size_t)n * MMIF_LOSS_PER_SAMPLE;
+            so[0] = t[0] * inv; so[1] = t[2] * inv; so[2] = t[4] * inv;   // ssim1, cs1, sigma1
+            so[3] = t[1] * inv; so[4] = t[3] * inv; so[5] = t[5] * inv;   // ssim2, cs2, sigma2
+            __threadfence();
+            const unsigned prev = atomicAdd(&p.counters[p.B], 1u);
+            if (prev == (unsigned)(p.B - 1)) {
+                __threadfence();
+                double a1 = 0.0, a2 = 0.0, px = 0.0, gr = 0.0;
+                for (int k = 0; k < p.B; ++k) {
+                    const double* q = p.sums + (size_t)k * p.sums_stride;
+                    a1 += __ldcg(q + 0) * inv; a2 += __ldcg(q + 1) * inv; px += __ldcg(q + 6); gr += __ldcg(q + 7);
+                }
+                const double npx = (double)p.B * (double)p.H * (double)p.W;
+                const double l_ssim = (double)p.w_ssim * (1.0 - 0.5 * (a1 / p.B + a2 / p.B));
+                const double l_pix = (double)p.w_pixel * px / npx;
+                const double l_grad = (double)p.w_grad * gr / npx;
+                p.out[MMIF_LOSS_SSIM] = l_ssim;
+                p.out[MMIF_LOSS_PIXEL] = l_pix;
+                p.out[MMIF_LOSS_GRAD] = l_grad;
+                p.out[MMIF_LOSS_TOTAL] = l_ssim + l_pix + l_grad;
+                p.counters[p.B] = 0u;
+            }
+        }
+    }
+}
+#endif
+
 struct FwdParams {
     const float* x1; const float* x2; const float* y;
+    FinishParams fin;
     int B, H, W, Hout, Wout;
     int seg_rows, nseg, nstrip;
     Taps taps;
@@ -33,12 +108,6 @@ struct FwdParams {
     float w_ssim, w_pixel, w_grad;
     int use_tma;
     int do_sobel;            // EPI_SSIM only: also accumulate the Sobel / pixel terms
-    int finalize;            // FIN_SUMS / FIN_LOSS
-    unsigned* counters;      // [B+1], zero on entry, left zero
-    double* partial;         // [B][nblk][8]
-    double* sums;            // per-sample raw sums: sums[n*sums_stride + 0..7]
-    long long sums_stride;
-    double* out;             // FIN_LOSS: loss block (mmif_b200.h MMIF_LOSS_*)
 };
 
 static inline size_t ws_counters_bytes(int B) { return (size_t)(((B + 1) * 4 + 255) / 256) * 256; }
@@ -236,60 +305,7 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
     // SSIM: [ssim1, ssim2, cs1, cs2, sig1, sig2, pix, grad]; VIF: [num1, den1, num2, den2, numsel, densel, 0, 0]
     double v[8] = {(double)s0.x, (double)s0.y, (double)s1.x, (double)s1.y, (double)s2.x, (double)s2.y,
                    (double)pix_sum, (double)grad_sum};
-    block_sum<8, kNT>(v, sm.red);
-    const int nblk = p.nstrip * p.nseg;
-    const int blk = seg * p.nstrip + strip;
-    if (threadIdx.x == 0) {
-        double* dst = p.partial + ((size_t)n * nblk + blk) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = v[i];
-        __threadfence();
-        const unsigned prev = atomicAdd(&p.counters[n], 1u);
-        sm.flag = (prev == (unsigned)(nblk - 1));
-    }
-    __syncthreads();
-    if (!sm.flag) return;
-    __threadfence();
-    double t[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = 0.0;
-    for (int k = threadIdx.x; k < nblk; k += kNT) {
-        const double* srcp = p.partial + ((size_t)n * nblk + k) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] += __ldcg(srcp + i);
-    }
-    block_sum<8, kNT>(t, sm.red);
-    if (threadIdx.x == 0) {
-        double* sums = p.sums + (size_t)n * p.sums_stride;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sums[i] = t[i];
-        p.counters[n] = 0u;
-        if (p.finalize == FIN_LOSS) {
-            const double inv = 1.0 / ((double)p.Hout * (double)p.Wout);
-            double* so = p.out + MMIF_LOSS_HEAD + (size_t)n * MMIF_LOSS_PER_SAMPLE;
-            so[0] = t[0] * inv; so[1] = t[2] * inv; so[2] = t[4] * inv;   // ssim1, cs1, sigma1
-            so[3] = t[1] * inv; so[4] = t[3] * inv; so[5] = t[5] * inv;   // ssim2, cs2, sigma2
-            __threadfence();
-            const unsigned prev = atomicAdd(&p.counters[p.B], 1u);
-            if (prev == (unsigned)(p.B - 1)) {
-                __threadfence();
-                double a1 = 0.0, a2 = 0.0, px = 0.0, gr = 0.0;
-                for (int k = 0; k < p.B; ++k) {
-                    const double* q = p.sums + (size_t)k * p.sums_stride;
-                    a1 += __ldcg(q + 0) * inv; a2 += __ldcg(q + 1) * inv; px += __ldcg(q + 6); gr += __ldcg(q + 7);
-                }
-                const double npx = (double)p.B * (double)p.H * (double)p.W;
-                const double l_ssim = (double)p.w_ssim * (1.0 - 0.5 * (a1 / p.B + a2 / p.B));
-                const double l_pix = (double)p.w_pixel * px / npx;
-                const double l_grad = (double)p.w_grad * gr / npx;
-                p.out[MMIF_LOSS_SSIM] = l_ssim;
-                p.out[MMIF_LOSS_PIXEL] = l_pix;
-                p.out[MMIF_LOSS_GRAD] = l_grad;
-                p.out[MMIF_LOSS_TOTAL] = l_ssim + l_pix + l_grad;
-                p.counters[p.B] = 0u;
-            }
-        }
-    }
+    cta_finish<kNT>(p.fin, v, sm.red, &sm.flag, n, seg * p.nstrip + strip, p.nstrip * p.nseg);
 }
 
 // ---- host-side geometry + launcher (defined in moment_fwd.cu) ----------------------------------

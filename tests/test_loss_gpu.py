@@ -158,3 +158,27 @@ def test_backward_is_linear_in_upstream_and_deterministic():
     assert torch.equal(tot, tot2)
     v1 = ML.SSIMLoss('ssim')(a, b, f.detach().clone()).item()
     assert v1 == l1.item()
+
+
+def test_single_pass_equals_two_kernel_path():
+    """The single-pass forward (loss + gradient in one launch, rescaled in backward) and the
+    two-kernel path (forward, recomputing backward) are the same numbers."""
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_2x150x260'))
+    res = {}
+    for single in (True, False):
+        ML.SINGLE_PASS = single
+        try:
+            A, B_, F_ = a.cuda(), b.cuda(), f.cuda().requires_grad_(True)
+            tot = ML.SSIMLoss('ssim', weight=1.0)(A, B_, F_) + ML.PixelLoss('l1', 0.01)(A, B_, F_, mode='max') \
+                + ML.GradLoss('l1', 0.1)(A, B_, F_, mode='max')
+            (2.5 * tot).backward()
+            res[single] = (tot.item(), F_.grad.cpu().numpy())
+        finally:
+            ML.SINGLE_PASS = True
+    assert abs(res[True][0] - res[False][0]) <= 2e-7 * abs(res[False][0])
+    scale = np.abs(res[False][1]).max()
+    assert np.abs(res[True][1] - res[False][1]).max() <= 1e-6 * scale
+    ref = 2.5 * LG['rand_2x150x260/f64/grad'].sum(axis=0)
+    frac, mx, where = gates.grad_report(res[True][1], ref)
+    assert frac <= 1e-4, (frac, mx, where)

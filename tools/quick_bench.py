@@ -27,8 +27,13 @@ for (B, H, W) in shapes:
     g = torch.ones(3, device='cuda'); dF = torch.empty_like(f)
     st = L.stream_ptr(a.device)
     fwd = lambda: L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(), None, ws.data_ptr(), ws.numel(), st))
-    bwd = lambda: L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), g.data_ptr(), dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    bwd = lambda: L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), g.data_ptr(), None, dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    cfgz = ML._cfg(1.0, 'max', 'max', 'l1', 'l1'); cfgz.want_grad = 1
+    dU = torch.empty_like(f)
+    zfwd = lambda: L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfgz), out.data_ptr(), dU.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    zbwd = lambda: L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), g.data_ptr(), dU.data_ptr(), dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
     tf, tb = timeit(fwd), timeit(bwd)
+    tzf, tzb = timeit(zfwd), timeit(zbwd)
     mp = B * H * W / 1e6
     print(f'{B}x{H}x{W}: fwd {tf:.3f} ms ({mp/tf/1e3*1e3:.1f} Mpix/ms = {mp/tf:.0f} Gpix/s*1e-3) bwd {tb:.3f} ms  fwd+bwd {mp/(tf+tb)*1e3:.0f} Mpix/s  '
-          f'GB/s fwd {12*mp/tf/1e3*1e3/1e3:.0f} bwd {16*mp/tb:.0f} both {28*mp/(tf+tb):.0f}')
+          f'GB/s bwd {16*mp/tb:.0f} both {28*mp/(tf+tb):.0f} | single-pass: fwd+grad {tzf:.3f} ms rescale {tzb:.3f} ms -> {mp/(tzf+tzb)*1e3:.0f} Mpix/s ({16*mp/tzf:.0f} GB/s @16B/px)')
