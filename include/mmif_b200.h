@@ -106,9 +106,30 @@ int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B
                          const MmifLossCfg* cfg, const float* gout3, const float* dF_unit, float* dF,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* d/dIf of  scale * sum_n sum_k pair_w[n][k] * mean_windows(S_k)(I_k[n], If[n]),  S = ssim or (cs_only) the
+ * contrast-structure term, times the device scalar gout1[0].  pair_w: [B][2] device floats or NULL (= 1).
+ * Building block of SSIMLoss('w-ssim') (loss.py:259-266: per-sample gamma from the sources) and of the
+ * MS-SSIM levels (loss.py:140-158: cs on levels 0..3, ssim on level 4, per-sample chain-rule factors). */
+int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
+                     const float* gout1, const float* pair_w, int cs_only, float scale, float* dF,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* MS-SSIM level step of the loss (loss.py:147-153): reflect-pad the odd edge, 2x2 mean; dst is
+ * [N][(H+1)/2][(W+1)/2].  mmif_halve_bwd ACCUMULATES the adjoint into g_src. */
+int mmif_halve(const float* src, int N, int H, int W, float* dst, void* stream);
+int mmif_halve_bwd(const float* g_dst, int N, int H, int W, float* g_src_accum, void* stream);
+
+/* F.pad(img, (p,p,p,p), 'reflect') of use_padding=True (loss.py:45-47) and its adjoint (writes g_src). */
+int mmif_reflect_pad(const float* src, int N, int H, int W, int pad, float* dst, void* stream);
+int mmif_reflect_pad_bwd(const float* g_dst, int N, int H, int W, int pad, float* g_src, void* stream);
+
 /* TVLoss.forward (loss.py:347-358) on x [N][H][W]: out[0] = w*(norm(dv) + norm(dh)). */
 int mmif_tv_loss(const float* x, int N, int H, int W, int norm, float weight, double* out,
                  void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of TVLoss (loss.py:347-358): gx = gout1[0] * d(tv)/dx, x and gx [N][H][W]. */
+int mmif_tv_loss_bwd(const float* x, int N, int H, int W, int norm, float weight, const float* gout1, float* gx,
+                     void* stream);
 
 /* ---------------------------------------------------------------- metric suite ----------- */
 /* All metric entries are batched over N independent pairs (a[n], b[n], f[n]) of one shape and

@@ -7,8 +7,10 @@ training modules share ONE fused forward launch and ONE backward launch per step
 kernel, the other two read their scalar from the same result (memo keyed on tensor identity and
 version), and a single autograd node with three outputs receives all three upstream gradients.
 
-Not built yet (raise NotImplementedError, never a silent fallback): 'w-ssim' backward,
-'ms-ssim', 'msw-ssim', use_padding=True, gradients w.r.t. the source images.
+Built on the same kernels: 'w-ssim' (per-sample gamma weights in the backward kernel), 'ms-ssim'
+(one SSIM forward/backward launch per pyramid level + pooling adjoints), use_padding=True (reflect-pad
+operator + its adjoint), TVLoss forward/backward.  Not built yet (raise NotImplementedError, never a
+silent fallback): 'msw-ssim', size_average=False, gradients w.r.t. the source images.
 """
 import ctypes
 import weakref
@@ -129,6 +131,193 @@ def _fused(img1, img2, imgf, data_range=None, pixel=None, grad=None, w_ssim=None
     return _memo.lookup(img1, img2, imgf, cfg_key)
 
 
+def _fwd_per_sample(x1, x2, y, data_range):
+    """Fused forward (no gradient) -> (B, 6) float64 per-sample means: ssim1, cs1, sigma1, ssim2, cs2, sigma2."""
+    lib = L.load()
+    B, H, W = y.shape
+    dev = y.device
+    cfg = _cfg(data_range, 'max', 'max', 'l1', 'l1')
+    out = torch.empty(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device=dev)
+    nws = lib.mmif_loss_workspace_bytes(B, H, W)
+    if nws == 0:
+        raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11 at every level')
+    ws = L.workspace(dev, nws, 'loss', (B, H, W))
+    with torch.cuda.device(dev):
+        L.check(lib.mmif_fusion_loss_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(),
+                                         None, ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+    return out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
+
+
+def _ssim_bwd_ex(x1, x2, y, data_range, gout1, pair_w, cs_only, scale):
+    lib = L.load()
+    B, H, W = y.shape
+    dev = y.device
+    dF = torch.empty_like(y)
+    ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
+    pw = pair_w.to(torch.float32).contiguous() if pair_w is not None else None
+    with torch.cuda.device(dev):
+        L.check(lib.mmif_ssim_bwd_ex(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, float(data_range), gout1.data_ptr(),
+                                     pw.data_ptr() if pw is not None else None, int(cs_only), float(scale), dF.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+    return dF
+
+
+def _prep3(img1, img2, imgf):
+    for t, nm in ((img1, 'img1'), (img2, 'img2'), (imgf, 'imgf')):
+        L.require_cuda(t, nm)
+    if img1.requires_grad or img2.requires_grad:
+        raise NotImplementedError('gradients w.r.t. the source images are not built (train.py never needs them)')
+    x1, B, H, W = L.as_f32_3d(img1.detach(), 'img1')
+    x2, _, _, _ = L.as_f32_3d(img2.detach(), 'img2')
+    y, _, _, _ = L.as_f32_3d(imgf.detach(), 'imgf')
+    if x2.shape != x1.shape or y.shape != x1.shape:
+        raise L.MmifError(f'shape mismatch: {tuple(img1.shape)} {tuple(img2.shape)} {tuple(imgf.shape)}')
+    L.ensure_device(y.device)
+    return x1.view(B, H, W), x2.view(B, H, W), y.view(B, H, W)
+
+
+class _WeightedSSIM(torch.autograd.Function):
+    """SSIMLoss('w-ssim') (loss.py:259-266): gamma_b = sigma1_b / (sigma1_b + sigma2_b) comes from the
+    SOURCE images only, so it is a per-sample constant of the backward."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, imgf, data_range):
+        x1, x2, y = _prep3(img1, img2, imgf)
+        ps = _fwd_per_sample(x1, x2, y, data_range).to(torch.float32)
+        gamma = ps[:, 2] / (ps[:, 2] + ps[:, 5]).clamp_(min=eps)
+        ctx.save_for_backward(x1, x2, y, gamma)
+        ctx.data_range, ctx.in_shape = data_range, imgf.shape
+        return (gamma * ps[:, 0]).mean() + ((1.0 - gamma) * ps[:, 3]).mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, y, gamma = ctx.saved_tensors
+        pw = torch.stack([gamma, 1.0 - gamma], dim=1)
+        g1 = g.to(torch.float32).reshape(1).contiguous()
+        dF = _ssim_bwd_ex(x1, x2, y, ctx.data_range, g1, pw, 0, 1.0 / y.shape[0])
+        return None, None, dF.view(ctx.in_shape), None
+
+
+def _halve(x):
+    lib = L.load()
+    B, H, W = x.shape
+    out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(lib.mmif_halve(x.data_ptr(), B, H, W, out.data_ptr(), L.stream_ptr(x.device)))
+    return out
+
+
+class _MSSSIM(torch.autograd.Function):
+    """calc_msssim of the loss module (loss.py:113-160) for the pairs (img1, imgf), (img2, imgf):
+    returns the two per-sample MS-SSIM vectors.  Backward: one SSIM-backward launch per level (cs on
+    levels 0..3, ssim on level 4, per-sample chain-rule factors) + the pooling adjoints."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, imgf, data_range):
+        x1, x2, y = _prep3(img1, img2, imgf)
+        wts = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float32, device=y.device)
+        levels, vals = [], []
+        for lvl in range(5):
+            if min(y.shape[-2:]) < 11:
+                raise L.MmifError(f'ms-ssim: level {lvl} is {tuple(y.shape[-2:])}, smaller than the 11-tap window '
+                                  '(the reference fails here too)')
+            ps = _fwd_per_sample(x1, x2, y, data_range)
+            vals.append(torch.stack([ps[:, 1], ps[:, 4]], dim=1) if lvl < 4 else torch.stack([ps[:, 0], ps[:, 3]], dim=1))
+            levels.append((x1, x2, y))
+            if lvl < 4:
+                x1, x2, y = _halve(x1), _halve(x2), _halve(y)
+        v = torch.stack(vals, dim=0).to(torch.float32)              # (5, B, 2)
+        vc = v.clamp(min=eps)
+        ms = torch.prod(vc ** wts.view(5, 1, 1), dim=0)              # (B, 2)
+        ctx.levels, ctx.data_range, ctx.in_shape = levels, data_range, imgf.shape
+        ctx.save_for_backward(v, vc, ms, wts)
+        return ms[:, 0].contiguous(), ms[:, 1].contiguous()
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        lib = L.load()
+        v, vc, ms, wts = ctx.saved_tensors
+        B = ms.shape[0]
+        zero = torch.zeros(B, dtype=torch.float32, device=ms.device)
+        g = torch.stack([zero if g1 is None else g1.to(torch.float32), zero if g2 is None else g2.to(torch.float32)], dim=1)
+        one = torch.ones(1, dtype=torch.float32, device=ms.device)
+        fac = g.unsqueeze(0) * wts.view(5, 1, 1) * ms.unsqueeze(0) / vc * (v >= eps).to(torch.float32)   # (5, B, 2)
+        grads = []
+        for lvl, (x1, x2, y) in enumerate(ctx.levels):
+            grads.append(_ssim_bwd_ex(x1, x2, y, ctx.data_range, one, fac[lvl], 1 if lvl < 4 else 0, 1.0))
+        for lvl in range(4, 0, -1):
+            Bn, H, W = grads[lvl - 1].shape
+            with torch.cuda.device(ms.device):
+                L.check(lib.mmif_halve_bwd(grads[lvl].data_ptr(), Bn, H, W, grads[lvl - 1].data_ptr(), L.stream_ptr(ms.device)))
+        return None, None, grads[0].view(ctx.in_shape), None
+
+
+class _ReflectPad(torch.autograd.Function):
+    """F.pad(img, (p,p,p,p), 'reflect') of use_padding=True (loss.py:45-47)."""
+
+    @staticmethod
+    def forward(ctx, img, pad):
+        lib = L.load()
+        L.require_cuda(img, 'img')
+        x, B, H, W = L.as_f32_3d(img.detach(), 'img')
+        out = torch.empty(B, 1, H + 2 * pad, W + 2 * pad, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.mmif_reflect_pad(x.data_ptr(), B, H, W, pad, out.data_ptr(), L.stream_ptr(x.device)))
+        ctx.dims, ctx.pad, ctx.in_shape = (B, H, W), pad, img.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        B, H, W = ctx.dims
+        g = g.contiguous()
+        out = torch.empty(B, H, W, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            L.check(lib.mmif_reflect_pad_bwd(g.data_ptr(), B, H, W, ctx.pad, out.data_ptr(), L.stream_ptr(g.device)))
+        return out.view(ctx.in_shape), None
+
+
+def _pad3(img1, img2, imgf, win_size=11):
+    p = win_size // 2
+    return _ReflectPad.apply(img1, p), _ReflectPad.apply(img2, p), _ReflectPad.apply(imgf, p)
+
+
+class _TV(torch.autograd.Function):
+    """TVLoss (loss.py:347-358) forward + backward."""
+
+    @staticmethod
+    def forward(ctx, x, norm, weight):
+        lib = L.load()
+        L.require_cuda(x, 'x')
+        if x.dim() < 2 or x.dtype != torch.float32:
+            raise L.MmifError('TVLoss needs a float32 tensor with at least 2 dims')
+        h, w = x.shape[-2:]
+        xc = x.detach().contiguous().view(-1, h, w)
+        dev = x.device
+        L.ensure_device(dev)
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+        n = xc.shape[0]
+        ws = L.workspace(dev, lib.mmif_metric_workspace_bytes(n, h, w), 'metric', (n, h, w))
+        with torch.cuda.device(dev):
+            L.check(lib.mmif_tv_loss(xc.data_ptr(), n, h, w, L.NORM[norm], float(weight), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     L.stream_ptr(dev)))
+        ctx.save_for_backward(xc)
+        ctx.norm, ctx.weight, ctx.in_shape = norm, weight, x.shape
+        return out[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        xc, = ctx.saved_tensors
+        n, h, w = xc.shape
+        gx = torch.empty_like(xc)
+        g1 = g.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(xc.device):
+            L.check(lib.mmif_tv_loss_bwd(xc.data_ptr(), n, h, w, L.NORM[ctx.norm], float(ctx.weight), g1.data_ptr(), gx.data_ptr(),
+                                         L.stream_ptr(xc.device)))
+        return gx.view(ctx.in_shape), None, None
+
+
 def _check_norm(mode):
     if mode not in ('l1', 'l2'):
         raise ValueError("only supported ['l1', 'l2'] mode")
@@ -143,7 +332,10 @@ def _auto_range(img):
 
 def _ssim_dict(img1, img2, data_range, use_padding, size_average, win_size=11):
     if use_padding:
-        raise NotImplementedError('use_padding=True is not built yet')
+        if win_size != 11:
+            raise NotImplementedError('only the 11-tap window of the training objective is built')
+        img1, img2 = _ReflectPad.apply(img1, 5), _ReflectPad.apply(img2, 5)
+        use_padding = False
     if not size_average:
         raise NotImplementedError('size_average=False (per-pixel SSIM maps) is not built yet')
     if win_size != 11:
@@ -180,7 +372,14 @@ class MS_SSIM(SSIM):
         self.register_buffer('weights', torch.FloatTensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333]))
 
     def forward(self, img1, img2):
-        raise NotImplementedError('MS_SSIM (loss) is not built yet; core.metric.calc_msssim is')
+        if self.win_size != 11:
+            raise NotImplementedError('only the 11-tap window of the training objective is built')
+        if not self.size_average:
+            raise NotImplementedError('size_average=False is not built yet')
+        if self.use_padding:
+            img1, img2 = _ReflectPad.apply(img1, 5), _ReflectPad.apply(img2, 5)
+        dr = _auto_range(img1) if self.data_range is None else self.data_range
+        return _MSSSIM.apply(img1, img1, img2, dr)[0]
 
 
 class MSW_SSIM(nn.Module):
@@ -208,22 +407,19 @@ class SSIMLoss(nn.Module):
         self.weight = weight
 
     def forward(self, img1, img2, imgf):
+        if self.mode in ('ssim', 'w-ssim', 'ms-ssim') and self.use_padding:
+            img1, img2, imgf = _pad3(img1, img2, imgf)      # reflect pad 5, then the valid-window path (loss.py:45-47)
         if self.mode == 'ssim':
-            if self.use_padding:
-                raise NotImplementedError('use_padding=True is not built yet')
             loss, _, _, _ = _fused(img1, img2, imgf, data_range=self.data_range, w_ssim=self.weight)
             return loss
         elif self.mode == 'w-ssim':
-            if self.use_padding:
-                raise NotImplementedError('use_padding=True is not built yet')
-            if imgf.requires_grad and torch.is_grad_enabled():
-                raise NotImplementedError("'w-ssim' backward is not built yet")
-            _, _, _, ps = _fused(img1, img2, imgf, data_range=self.data_range)
-            gamma = ps[:, 2] / (ps[:, 2] + ps[:, 5]).clamp_(min=eps)
-            loss = (gamma * ps[:, 0]).mean() + ((1.0 - gamma) * ps[:, 3]).mean()
+            loss = _WeightedSSIM.apply(img1, img2, imgf, self.data_range)
             return self.weight * (1.0 - loss)
-        elif self.mode in ('ms-ssim', 'msw-ssim'):
-            raise NotImplementedError(f"SSIMLoss mode '{self.mode}' is not built yet")
+        elif self.mode == 'ms-ssim':
+            m1, m2 = _MSSSIM.apply(img1, img2, imgf, self.data_range)
+            return self.weight * (1.0 - (m1.mean() + m2.mean()) * 0.5)
+        elif self.mode == 'msw-ssim':
+            raise NotImplementedError("SSIMLoss mode 'msw-ssim' is not built yet")
         else:
             raise ValueError("only supported ['ssim', 'w-ssim', 'ms-ssim', 'msw-ssim'] mode")
 
@@ -275,24 +471,7 @@ class TVLoss(nn.Module):
 
     def forward(self, x):
         _check_norm(self.mode)
-        if x.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError('TVLoss backward is not built yet (no reference script uses TVLoss)')
-        L.require_cuda(x, 'x')
-        lib = L.load()
-        if x.dim() < 2:
-            raise L.MmifError('TVLoss needs at least 2 dims')
-        h, w = x.shape[-2:]
-        xc = x.contiguous().view(-1, h, w)
-        if xc.dtype != torch.float32:
-            raise L.MmifError('float32 expected')
-        dev = x.device
-        L.ensure_device(dev)
-        out = torch.empty(1, dtype=torch.float64, device=dev)
-        ws = L.workspace(dev, lib.mmif_metric_workspace_bytes(xc.shape[0], h, w), 'metric', (xc.shape[0], h, w))
-        with torch.cuda.device(dev):
-            L.check(lib.mmif_tv_loss(xc.data_ptr(), xc.shape[0], h, w, L.NORM[self.mode], float(self.weight),
-                                     out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
-        return out[0].to(torch.float32)
+        return _TV.apply(x, self.mode, self.weight)
 
 
 class NormLoss(nn.Module):

@@ -41,6 +41,10 @@ struct BwdParams {
     float w_ssim, w_pixel, w_grad;
     int use_tma;
     int vec_store;
+    const float* pair_w;     // nullptr or [B][2]: per-sample weights of the two SSIM pairs ('w-ssim', MS-SSIM levels)
+    float ssim_base;         // k_ssim = g[0] * ssim_base / (Hout*Wout); default w_ssim * (-0.5) / B
+    int cs_only;             // differentiate the contrast-structure term only (MS-SSIM levels 0..3, loss.py:144-145)
+    int do_sobel;            // 0: SSIM term only (no pixel / Sobel adjoint)
     const float* dF_unit;    // != nullptr: gradient already computed for unit upstream (single-pass forward);
                              // if the three upstream gradients are equal the kernel only rescales it
     FinishParams fin;        // ZMODE: loss sums / finish (same protocol as the forward kernel)
@@ -95,8 +99,9 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
     __syncthreads();
     const Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, R0, iend - R0 + HALO, jw0, p.taps);
-    const float g_ssim = p.gout ? __ldg(p.gout + 0) : 1.f, g_pix = p.gout ? __ldg(p.gout + 1) : 1.f,
-                g_grad = p.gout ? __ldg(p.gout + 2) : 1.f;
+    const bool rd3 = p.gout && p.do_sobel;       // the SSIM-only entry passes a single upstream scalar
+    const float g_ssim = p.gout ? __ldg(p.gout + 0) : 1.f, g_pix = rd3 ? __ldg(p.gout + 1) : (p.gout ? 0.f : 1.f),
+                g_grad = rd3 ? __ldg(p.gout + 2) : (p.gout ? 0.f : 1.f);
     if (!ZMODE && p.dF_unit != nullptr && g_ssim == g_pix && g_pix == g_grad) {
         // total = l1 + l2 + l3 (train.py:69): the upstream gradients are one common scalar, and the
         // single-pass forward already produced d(total)/dIf for unit upstream: rescale_unit_kernel
@@ -104,7 +109,8 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         return;
     }
     const float npx = (float)p.B * (float)p.H * (float)p.W;
-    const float k_ssim = g_ssim * p.w_ssim * (-0.5f) / ((float)p.B * (float)p.Hout * (float)p.Wout);
+    const float k_ssim = g_ssim * p.ssim_base / ((float)p.Hout * (float)p.Wout);
+    const float2 pairw = p.pair_w ? f2(__ldg(p.pair_w + 2 * n), __ldg(p.pair_w + 2 * n + 1)) : f2(1.f, 1.f);
     const float k_pix = g_pix * p.w_pixel / npx * (p.pixel_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
     const float k_grad = g_grad * p.w_grad / npx * (p.grad_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
 
@@ -122,6 +128,9 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
 #pragma unroll
     for (int d = 0; d < HALO; ++d) carry[d][0] = carry[d][1] = f2(0.f, 0.f);
 
+    if (!p.do_sobel) {
+        for (int i = t; i < kRB * (kTMC + 4); i += kNT) (&sb.gbuf[0][0])[i] = 0.f;     // B2 adds gbuf unconditionally
+    }
     // Sobel-adjoint phase: column of this thread and its sliding state
     const int s_ci = 30 * warp + lane - 1;            // column relative to j0: -1 .. 120 (lanes 0 / 31 are halo lanes)
     const int s_c = j0 + s_ci;
@@ -146,7 +155,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         // thread = column (warps own 30 columns + 1 halo lane each side); one input row per step:
         // input row q' -> Sobel / tx,ty of row q'-1 -> (neighbour columns by shuffle) -> G of row q'-2.
         // All sliding state lives in registers across batches, so every input row is visited once.
-        {
+        if (p.do_sobel) {
 #pragma unroll 2
             for (int step = 0; step < kRB; ++step) {
                 const int qp = Rb + 2 + step;                       // input row q'
@@ -232,16 +241,24 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                         const float2 rB1 = fdiv_nr2(bcast(1.f), B1);
                         const float2 rB2 = fdiv_nr2(bcast(1.f), B2);
                         const float2 rBB = mul2(rB1, rB2);
-                        const float2 S = mul2(mul2(A1, A2), rBB);
-                        const float2 dcov = mul2(muls(2.f, A1), rBB);                    // dS/dcov
-                        const float2 dvar = muls(-myk, mul2(S, rB2));                    // dS/dvar_y
-                        // dS/dmu_y (luminance path) = 2 mu_k A2/(B1 B2) - 2 mu_y S / B1
-                        const float2 dmu = fma2(mul2(muls(2.f, st.mu), A2), rBB, muls(-2.f * st.muy, mul2(S, rB1)));
+                        float2 S, dcov, dvar, dmu;
+                        if (p.cs_only) {                                                 // S = cs = A2 / B2
+                            S = mul2(A2, rB2);
+                            dcov = muls(2.f, rB2);
+                            dvar = muls(-myk, mul2(S, rB2));
+                            dmu = f2(0.f, 0.f);
+                        } else {
+                            S = mul2(mul2(A1, A2), rBB);
+                            dcov = mul2(muls(2.f, A1), rBB);                             // dS/dcov
+                            dvar = muls(-myk, mul2(S, rB2));                             // dS/dvar_y
+                            // dS/dmu_y (luminance path) = 2 mu_k A2/(B1 B2) - 2 mu_y S / B1
+                            dmu = fma2(mul2(muls(2.f, st.mu), A2), rBB, muls(-2.f * st.muy, mul2(S, rB1)));
+                        }
                         // a' = dmu - dvar (2 my' + 2 eps cy) - dcov (mk' + eps ck)
                         const float2 a = fma2(muls(-1.f, dcov), add2(mo.mk, sh.ec),
                                               fma2(muls(-1.f, dvar), bcast(2.f * mo.my + sh.k1y), dmu));
-                        ab[j] = f2(a.x + a.y, dvar.x + dvar.y);
-                        cc[j] = dcov;
+                        ab[j] = f2(pairw.x * a.x + pairw.y * a.y, pairw.x * dvar.x + pairw.y * dvar.y);
+                        cc[j] = mul2(dcov, pairw);
                         if (ZMODE && q >= i0 && q < iend && pc >= j0 && pc < jend) {
                             z_ss = add2(z_ss, S);
                             z_cs = add2(z_cs, mul2(A2, rB2));
@@ -408,9 +425,11 @@ extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
 }
 extern "C" size_t mmif_loss_out_doubles(int B) { return (size_t)MMIF_LOSS_HEAD + (size_t)(B > 0 ? B : 0) * MMIF_LOSS_PER_SAMPLE; }
 
+struct BwdExtra { const float* pair_w; float ssim_base; int cs_only; int do_sobel; bool use_base; };
+
 static int launch_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, const MmifLossCfg* cfg,
                       const float* gout3, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, const BwdExtra* ex = nullptr) {
     const BwdGeom g = bwd_geom(B, H, W);
     BwdParams p;
     memset(&p, 0, sizeof(p));
@@ -424,6 +443,12 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     p.pixel_norm = cfg->pixel_norm; p.grad_norm = cfg->grad_norm;
     p.w_ssim = cfg->w_ssim; p.w_pixel = cfg->w_pixel; p.w_grad = cfg->w_grad;
     p.vec_store = ((W & 3) == 0) && ((((uintptr_t)dF) & 15) == 0);
+    p.ssim_base = cfg->w_ssim * (-0.5f) / (float)B;
+    p.do_sobel = 1;
+    if (ex) {
+        p.pair_w = ex->pair_w; p.cs_only = ex->cs_only; p.do_sobel = ex->do_sobel;
+        if (ex->use_base) p.ssim_base = ex->ssim_base;
+    }
     if (zmode) {
         const size_t core = loss_ws_core_bytes(B, H, W);
         if (!ws || ws_bytes < core + (size_t)B * 8 * sizeof(double)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
@@ -502,4 +527,23 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     if ((((uintptr_t)dF) | ((uintptr_t)dF_unit)) & 3) { set_error("dF / dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
     if (dF_unit == dF) { set_error("dF must not alias dF_unit"); return MMIF_E_MODE; }
     return launch_bwd(i1, i2, f, B, H, W, cfg, gout3, dF_unit, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+/* d/dIf of  scale * sum_n sum_k pair_w[n][k] * mean_windows(S_k or cs_k)(I_k[n], If[n])  times the device
+ * scalar gout1[0]: the building block of 'w-ssim' (loss.py:259-266, per-sample gamma) and of the
+ * MS-SSIM levels (loss.py:140-158: cs on levels 0..3, ssim on level 4, per-sample chain-rule factors). */
+extern "C" int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
+                                const float* gout1, const float* pair_w, int cs_only, float scale, float* dF, void* ws,
+                                size_t ws_bytes, void* stream) {
+    int rc = check_common(i1, i2, f, B, H, W);
+    if (rc) return rc;
+    if (!gout1 || !dF) { set_error("null gout1/dF"); return MMIF_E_NULL; }
+    if (((uintptr_t)dF | (uintptr_t)pair_w) & 3) { set_error("dF / pair_w must be 4-byte aligned"); return MMIF_E_ALIGN; }
+    MmifLossCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.w_ssim = 1.f; cfg.data_range = data_range;
+    cfg.pixel_combine = cfg.grad_combine = MMIF_COMBINE_MAX; cfg.pixel_norm = cfg.grad_norm = MMIF_NORM_L1;
+    BwdExtra ex;
+    ex.pair_w = pair_w; ex.ssim_base = scale; ex.cs_only = cs_only; ex.do_sobel = 0; ex.use_base = true;
+    return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
 }

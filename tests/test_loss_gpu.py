@@ -121,7 +121,7 @@ def test_errors_match_reference():
         ML.PixelLoss('l3')(x, x, x, mode='max')
     assert ML.PixelLoss('l1')(x, x, x, mode='other') is None
     with pytest.raises(NotImplementedError):
-        ML.SSIMLoss('ms-ssim')(x, x, x)
+        ML.SSIMLoss('msw-ssim')(x, x, x)
     with pytest.raises(Exception):
         ML.SSIMLoss('ssim')(x.cpu(), x.cpu(), x.cpu())   # no CPU fallback
 
@@ -182,3 +182,63 @@ def test_single_pass_equals_two_kernel_path():
     ref = 2.5 * LG['rand_2x150x260/f64/grad'].sum(axis=0)
     frac, mx, where = gates.grad_report(res[True][1], ref)
     assert frac <= 1e-4, (frac, mx, where)
+
+
+def _grad_vs_oracle(loss_new_fn, loss_ref_fn, a, b, f, rtol=1e-5):
+    A, B_, F_ = a.cuda(), b.cuda(), f.cuda().requires_grad_(True)
+    ln = loss_new_fn(A, B_, F_)
+    gn, = torch.autograd.grad(ln, F_)
+    r32 = loss_ref_fn(a, b, f).item()
+    fd = f.double().requires_grad_(True)
+    l64 = loss_ref_fn(a.double(), b.double(), fd)
+    g64, = torch.autograd.grad(l64, fd)
+    f32 = f.clone().requires_grad_(True)
+    g32, = torch.autograd.grad(loss_ref_fn(a, b, f32), f32)
+    gates.assert_scalar('loss', ln.item(), r32, l64.item())
+    frac, mx, where = gates.grad_report(gn.cpu().numpy(), g64.numpy(), rtol)
+    ref_err = np.abs(g32.numpy() - g64.numpy()).max() / np.abs(g64.numpy()).max()
+    assert mx <= max(rtol, ref_err), f'grad max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+
+
+def test_w_ssim_forward_backward():
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('w-ssim', weight=0.7)(x1, x2, y),
+                    lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'w-ssim', weight=0.7), a, b, f)
+
+
+def test_ms_ssim_forward_backward():
+    ML = _mods()
+    g = torch.Generator().manual_seed(3)
+    a, b, f = (torch.rand(2, 1, 181, 200, generator=g) for _ in range(3))     # odd sizes down the pyramid: 181 -> 91 -> 46 -> 23 -> 12
+    f = (0.5 * (a + b) + 0.1 * f).contiguous()
+    _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('ms-ssim')(x1, x2, y),
+                    lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'ms-ssim'), a, b, f)
+    ms = ML.MS_SSIM()(a.cuda(), f.cuda())
+    ref = OL.msssim(a, f, window=OL.window2d(11, 1.5), data_range=1.0)
+    np.testing.assert_allclose(ms.cpu().numpy(), ref.numpy(), rtol=1e-5)
+
+
+def test_use_padding_forward_backward():
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_2x40x37'))
+    _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('ssim', use_padding=True)(x1, x2, y),
+                    lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'ssim', use_padding=True), a, b, f)
+    d = ML.SSIM(use_padding=True)(a.cuda(), f.cuda())
+    ref = OL.ssim(a, f, window=OL.window2d(11, 1.5), data_range=1.0, use_padding=True)
+    np.testing.assert_allclose(d['ssim'].cpu().numpy(), ref['ssim'].numpy(), rtol=1e-5)
+
+
+@pytest.mark.parametrize('mode', ['l1', 'l2'])
+def test_tv_loss_forward_backward(mode):
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_2x40x37'))
+    x = (f - a).cuda().requires_grad_(True)
+    l = ML.TVLoss(mode, weight=0.3)(x)
+    g, = torch.autograd.grad(l, x)
+    xd = (f - a).double().requires_grad_(True)
+    l64 = OL.tv_loss(xd, mode, 0.3)
+    g64, = torch.autograd.grad(l64, xd)
+    gates.assert_scalar('tv', l.item(), OL.tv_loss(f - a, mode, 0.3).item(), l64.item())
+    frac, mx, where = gates.grad_report(g.cpu().numpy(), g64.numpy())
+    assert frac <= (1e-3 if mode == 'l1' else 0.0), (frac, mx, where)
