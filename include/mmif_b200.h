@@ -114,6 +114,15 @@ int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f, int B, in
                      const float* gout1, const float* pair_w, int cs_only, float scale, float* dF,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* One window size (11, 9, 7, 5 or 3; sigma by the loss rule, loss.py:34) of MSW_SSIM.forward
+ * (loss.py:226-237): out_sums8[8*n] = sum over window positions of gamma*ssim(I1,If) + (1-gamma)*ssim(I2,If),
+ * gamma = sigma1/(sigma1+sigma2) per position.  mmif_mswssim_bwd: dF (+)= gout1[0] * scale *
+ * d( sum_n out_sums8[8n] / (Hout*Wout) )/dIf;  ws from mmif_loss_workspace_bytes. */
+int mmif_mswssim_fwd(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                     double* out_sums8, void* ws, size_t ws_bytes, void* stream);
+int mmif_mswssim_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                     const float* gout1, float scale, int accumulate, float* dF, void* ws, size_t ws_bytes, void* stream);
+
 /* MS-SSIM level step of the loss (loss.py:147-153): reflect-pad the odd edge, 2x2 mean; dst is
  * [N][(H+1)/2][(W+1)/2].  mmif_halve_bwd ACCUMULATES the adjoint into g_src. */
 int mmif_halve(const float* src, int N, int H, int W, float* dst, void* stream);

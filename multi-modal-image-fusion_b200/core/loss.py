@@ -10,7 +10,8 @@ version), and a single autograd node with three outputs receives all three upstr
 Built on the same kernels: 'w-ssim' (per-sample gamma weights in the backward kernel), 'ms-ssim'
 (one SSIM forward/backward launch per pyramid level + pooling adjoints), use_padding=True (reflect-pad
 operator + its adjoint), TVLoss forward/backward.  Not built yet (raise NotImplementedError, never a
-silent fallback): 'msw-ssim', size_average=False, gradients w.r.t. the source images.
+silent fallback): size_average=False (SSIM maps), MSW_SSIM with use_padding, gradients w.r.t. the sources.
+'msw-ssim' runs the same forward / backward kernels with the 11/9/7/5/3 windows and per-position weights.
 """
 import ctypes
 import weakref
@@ -252,6 +253,49 @@ class _MSSSIM(torch.autograd.Function):
         return None, None, grads[0].view(ctx.in_shape), None
 
 
+class _MSWSSIM(torch.autograd.Function):
+    """MSW_SSIM.forward (loss.py:226-237): windows 11/9/7/5/3 (sigma by loss.py:34), per-position
+    gamma = sigma1/(sigma1+sigma2) from the SOURCE variances (a constant of the backward)."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, imgf, data_range, win_sizes):
+        lib = L.load()
+        x1, x2, y = _prep3(img1, img2, imgf)
+        B, H, W = y.shape
+        dev = y.device
+        nws = lib.mmif_loss_workspace_bytes(B, H, W)
+        if nws == 0:
+            raise L.MmifError(f'unsupported shape {(B, H, W)}')
+        ws = L.workspace(dev, nws, 'loss', (B, H, W))
+        total = torch.zeros((), dtype=torch.float64, device=dev)
+        for k in win_sizes:
+            sums = torch.empty(B * 8, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                L.check(lib.mmif_mswssim_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(k), float(data_range),
+                                             sums.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+            total = total + sums.view(B, 8)[:, 0].sum() / (B * (H - k + 1) * (W - k + 1))
+        ctx.save_for_backward(x1, x2, y)
+        ctx.data_range, ctx.win_sizes, ctx.in_shape = data_range, tuple(win_sizes), imgf.shape
+        return (total / len(win_sizes)).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        x1, x2, y = ctx.saved_tensors
+        B, H, W = y.shape
+        dev = y.device
+        dF = torch.empty_like(y)
+        g1 = g.to(torch.float32).reshape(1).contiguous()
+        ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
+        scale = 1.0 / (B * len(ctx.win_sizes))
+        for i, k in enumerate(ctx.win_sizes):
+            with torch.cuda.device(dev):
+                L.check(lib.mmif_mswssim_bwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(k), float(ctx.data_range),
+                                             g1.data_ptr(), scale, 1 if i else 0, dF.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             L.stream_ptr(dev)))
+        return None, None, dF.view(ctx.in_shape), None, None
+
+
 class _ReflectPad(torch.autograd.Function):
     """F.pad(img, (p,p,p,p), 'reflect') of use_padding=True (loss.py:45-47)."""
 
@@ -393,7 +437,12 @@ class MSW_SSIM(nn.Module):
         self.size_average = size_average
 
     def forward(self, img1, img2, imgf):
-        raise NotImplementedError('MSW_SSIM is not built yet')
+        if any(k not in (11, 9, 7, 5, 3) for k in self.win_sizes):
+            raise NotImplementedError('MSW_SSIM: windows 11, 9, 7, 5, 3 are built')
+        if self.use_padding:
+            raise NotImplementedError('MSW_SSIM with use_padding=True is not built yet')
+        dr = _auto_range(img1) if self.data_range is None else self.data_range
+        return _MSWSSIM.apply(img1, img2, imgf, dr, tuple(self.win_sizes))
 
 
 class SSIMLoss(nn.Module):
@@ -419,7 +468,8 @@ class SSIMLoss(nn.Module):
             m1, m2 = _MSSSIM.apply(img1, img2, imgf, self.data_range)
             return self.weight * (1.0 - (m1.mean() + m2.mean()) * 0.5)
         elif self.mode == 'msw-ssim':
-            raise NotImplementedError("SSIMLoss mode 'msw-ssim' is not built yet")
+            loss = MSW_SSIM((11, 9, 7, 5, 3), self.data_range, self.use_padding)(img1, img2, imgf)
+            return self.weight * (1.0 - loss)
         else:
             raise ValueError("only supported ['ssim', 'w-ssim', 'ms-ssim', 'msw-ssim'] mode")
 

@@ -11,18 +11,24 @@
 
 namespace mmif {
 
-constexpr int WIN = 11;
-constexpr int HALO = WIN - 1;
-constexpr int kTWO = FwdGeo<WIN>::TWO;    // 116 SSIM-map columns per forward strip
-constexpr int kOFF = 12;                  // backward tile origin = j0 - 12 (TMA: multiple of 4 columns, >= HALO)
-constexpr int kTG = 104;                  // gradient columns per backward strip (104 + 12 + 10 <= 128, multiple of 4)
-constexpr int kWC = kTWI - HALO;          // 118 window columns carry valid moments in a backward tile
+constexpr int WIN11 = 11;
+// Backward tile geometry for a WIN-tap window: the tile origin is j0 - OFF (TMA: a multiple of 4
+// columns, >= HALO); TG gradient columns per strip (TG + OFF + HALO <= 128, multiple of 4); WC window
+// columns carry valid moments.  WIN = 11: OFF 12, TG 104, WC 118.
+template <int WIN>
+struct BG {
+    static constexpr int HALO = WIN - 1;
+    static constexpr int OFF = (HALO + 3) / 4 * 4;
+    static constexpr int TG = (kTWI - OFF - HALO) / 4 * 4;
+    static constexpr int WC = kTWI - HALO;
+};
+static int bwd_tg(int win) { const int halo = win - 1, off = (halo + 3) / 4 * 4; return (kTWI - off - halo) / 4 * 4; }
 
 struct BwdGeom { int Hout, Wout, seg_rows, nseg, nstrip; };
-static BwdGeom bwd_geom(int B, int H, int W) {
+static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
     BwdGeom g;
-    g.Hout = H - HALO; g.Wout = W - HALO;
-    g.nstrip = ceil_div(W, kTG);
+    g.Hout = H - (win - 1); g.Wout = W - (win - 1);
+    g.nstrip = ceil_div(W, bwd_tg(win));
     g.seg_rows = fwd_seg_rows(H, B * g.nstrip);
     g.nseg = ceil_div(H, g.seg_rows);
     return g;
@@ -44,6 +50,8 @@ struct BwdParams {
     const float* pair_w;     // nullptr or [B][2]: per-sample weights of the two SSIM pairs ('w-ssim', MS-SSIM levels)
     float ssim_base;         // k_ssim = g[0] * ssim_base / (Hout*Wout); default w_ssim * (-0.5) / B
     int cs_only;             // differentiate the contrast-structure term only (MS-SSIM levels 0..3, loss.py:144-145)
+    int msw;                 // MSW_SSIM (loss.py:226-237): per-window pair weights gamma, 1 - gamma from the source variances
+    int accum;               // dF += instead of dF =
     int do_sobel;            // 0: SSIM term only (no pixel / Sobel adjoint)
     const float* dF_unit;    // != nullptr: gradient already computed for unit upstream (single-pass forward);
                              // if the three upstream gradients are equal the kernel only rescales it
@@ -51,7 +59,7 @@ struct BwdParams {
 };
 
 constexpr int kCPitch = 2 * kTWI + 2;   // float2 units per coefficient row (2 pair-maps x 128 + 16 B pad)
-constexpr int kTMC = 112;               // tmaps / gbuf columns
+constexpr int kTMC = 120;               // gbuf columns (>= the widest gradient strip)
 
 constexpr int kRPB = kTWI + 4;           // backward ring row pitch (132 floats = 16 mod 128 B)
 using SmemB = SmemT<4, kRPB>;
@@ -64,17 +72,18 @@ __device__ __forceinline__ float mulsign(float r, float g) {
 struct SmemBwd {
     SmemB s;                             // ring + vbuf (vbuf also hosts the B1->B2 buffer)
     alignas(16) float2 cbuf[kRB * kCPitch];          // coefficient rows of the current batch: (a,b) and (c1,c2)
-    alignas(16) float gbuf[kRB][kTMC + 4];   // pixel + Sobel gradient of the batch rows (row pitch 464 B = 80 mod 128)
+    alignas(16) float gbuf[kRB][kTMC + 4];   // pixel + Sobel gradient of the batch rows (row pitch 496 B = 112 mod 128)
 };
 
 // FAST : mode='max' + 'l1' for both terms (train.py:67-68,307-308), no run-time mode switches.
 // ZMODE: single-pass variant — the same launch also accumulates the three loss values (every window
 //        position / pixel is owned by exactly one CTA: the one whose gradient tile contains it), so
 //        forward + backward cost one kernel and 16 B/pixel instead of two kernels and 28 B/pixel.
-template <bool FAST, bool ZMODE>
+template <int WIN, bool FAST, bool ZMODE>
 __global__ void __launch_bounds__(kNT, 2)
 fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
+    constexpr int HALO = BG<WIN>::HALO, kOFF = BG<WIN>::OFF, kTG = BG<WIN>::TG, kWC = BG<WIN>::WC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemBwd& sb = *reinterpret_cast<SmemBwd*>(smem_raw);
     SmemB& sm = sb.s;
@@ -257,8 +266,14 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                         // a' = dmu - dvar (2 my' + 2 eps cy) - dcov (mk' + eps ck)
                         const float2 a = fma2(muls(-1.f, dcov), add2(mo.mk, sh.ec),
                                               fma2(muls(-1.f, dvar), bcast(2.f * mo.my + sh.k1y), dmu));
-                        ab[j] = f2(pairw.x * a.x + pairw.y * a.y, pairw.x * dvar.x + pairw.y * dvar.y);
-                        cc[j] = mul2(dcov, pairw);
+                        float2 wq = pairw;
+                        if (p.msw) {                                                     // gamma = sigma1 / (sigma1 + sigma2), loss.py:232-233
+                            const float sg1 = fmaxf(vk.x, 1e-4f), sg2 = fmaxf(vk.y, 1e-4f);
+                            const float gm = __fdiv_rn(sg1, fmaxf(sg1 + sg2, 1e-7f));
+                            wq = f2(gm, 1.f - gm);
+                        }
+                        ab[j] = f2(wq.x * a.x + wq.y * a.y, wq.x * dvar.x + wq.y * dvar.y);
+                        cc[j] = mul2(dcov, wq);
                         if (ZMODE && q >= i0 && q < iend && pc >= j0 && pc < jend) {
                             z_ss = add2(z_ss, S);
                             z_cs = add2(z_cs, mul2(A2, rB2));
@@ -341,6 +356,11 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                     outv[j] = fmaf(k_ssim, dS, gb[j]);
                 }
                 float* dst = p.dF + img_off + (size_t)i * p.W + j0 + hg * 8;
+                if (p.accum) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j0 + hg * 8 + j < jend) outv[j] += dst[j];
+                }
                 if (p.vec_store && j0 + hg * 8 + 8 <= jend) {
                     reinterpret_cast<float4*>(dst)[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
                     reinterpret_cast<float4*>(dst)[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);
@@ -392,7 +412,7 @@ rescale_unit_kernel(const float* __restrict__ gout, const float* __restrict__ un
 // =============================================================================== host side
 static int check_common(const void* a, const void* b, const void* c, int B, int H, int W) {
     if (!a || !b || !c) { set_error("null image pointer"); return MMIF_E_NULL; }
-    if (B < 1 || H < WIN || W < WIN) { set_error("shape (%d,%d,%d): need B>=1 and H,W >= %d", B, H, W, WIN); return MMIF_E_SHAPE; }
+    if (B < 1 || H < WIN11 || W < WIN11) { set_error("shape (%d,%d,%d): need B>=1 and H,W >= %d", B, H, W, WIN11); return MMIF_E_SHAPE; }
     if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 3) { set_error("image pointers must be 4-byte aligned"); return MMIF_E_ALIGN; }
     return MMIF_OK;
 }
@@ -413,11 +433,17 @@ using namespace mmif;
 
 // workspace = [counters + partials (max of the forward / backward grids)][B x 8 per-sample sums]
 static size_t loss_ws_core_bytes(int B, int H, int W) {
-    const size_t f = fwd_ws_bytes(WIN, B, H, W);
-    if (!f) return 0;
-    const BwdGeom g = bwd_geom(B, H, W);
-    const size_t z = ws_counters_bytes(B) + (size_t)B * g.nstrip * g.nseg * 8 * sizeof(double);
-    return f > z ? f : z;
+    if (!fwd_ws_bytes(WIN11, B, H, W)) return 0;
+    size_t best = 0;
+    const int wins[5] = {11, 9, 7, 5, 3};          // MSW_SSIM runs the same kernels with the smaller windows
+    for (int k = 0; k < 5; ++k) {
+        const size_t f = fwd_ws_bytes(wins[k], B, H, W);
+        const BwdGeom g = bwd_geom(B, H, W, wins[k]);
+        const size_t z = ws_counters_bytes(B) + (size_t)B * g.nstrip * g.nseg * 8 * sizeof(double);
+        best = best > f ? best : f;
+        best = best > z ? best : z;
+    }
+    return best;
 }
 extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
     const size_t f = loss_ws_core_bytes(B, H, W);
@@ -425,18 +451,19 @@ extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
 }
 extern "C" size_t mmif_loss_out_doubles(int B) { return (size_t)MMIF_LOSS_HEAD + (size_t)(B > 0 ? B : 0) * MMIF_LOSS_PER_SAMPLE; }
 
-struct BwdExtra { const float* pair_w; float ssim_base; int cs_only; int do_sobel; bool use_base; };
+struct BwdExtra { const float* pair_w; float ssim_base; int cs_only; int do_sobel; bool use_base; int win; double sigma; int msw; int accum; };
 
 static int launch_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, const MmifLossCfg* cfg,
                       const float* gout3, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
                       cudaStream_t st, const BwdExtra* ex = nullptr) {
-    const BwdGeom g = bwd_geom(B, H, W);
+    const int win = (ex && ex->win) ? ex->win : WIN11;
+    const BwdGeom g = bwd_geom(B, H, W, win);
     BwdParams p;
     memset(&p, 0, sizeof(p));
     p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.gout = gout3; p.dF_unit = dF_unit;
     p.B = B; p.H = H; p.W = W; p.Hout = g.Hout; p.Wout = g.Wout;
     p.seg_rows = g.seg_rows; p.nseg = g.nseg; p.nstrip = g.nstrip;
-    make_taps(&p.taps, WIN, 1.5);
+    make_taps(&p.taps, win, (ex && ex->win) ? ex->sigma : 1.5);
     const double L = cfg->data_range;
     p.C1 = (float)((0.01 * L) * (0.01 * L)); p.C2 = (float)((0.03 * L) * (0.03 * L));
     p.pixel_combine = cfg->pixel_combine; p.grad_combine = cfg->grad_combine;
@@ -446,7 +473,7 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     p.ssim_base = cfg->w_ssim * (-0.5f) / (float)B;
     p.do_sobel = 1;
     if (ex) {
-        p.pair_w = ex->pair_w; p.cs_only = ex->cs_only; p.do_sobel = ex->do_sobel;
+        p.pair_w = ex->pair_w; p.cs_only = ex->cs_only; p.do_sobel = ex->do_sobel; p.msw = ex->msw; p.accum = ex->accum;
         if (ex->use_base) p.ssim_base = ex->ssim_base;
     }
     if (zmode) {
@@ -467,10 +494,14 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     static bool attr_done = false;
     if (!attr_done) {
         const int sz = (int)sizeof(SmemBwd);
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<9, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<7, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
         attr_done = true;
     }
     dim3 grid(g.nstrip, g.nseg, B);
@@ -481,14 +512,23 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaGetLastError());
     }
     const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
-                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
+                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1 && p.do_sobel;
     const size_t sm = sizeof(SmemBwd);
-    if (zmode) {
-        if (fast) fusion_loss_bwd_kernel<true, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
-        else fusion_loss_bwd_kernel<false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+    if (win != 11) {
+        if (zmode || p.do_sobel) { set_error("window %d: only the SSIM-only backward is instantiated", win); return MMIF_E_MODE; }
+        switch (win) {
+            case 9: fusion_loss_bwd_kernel<9, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 7: fusion_loss_bwd_kernel<7, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 5: fusion_loss_bwd_kernel<5, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 3: fusion_loss_bwd_kernel<3, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            default: set_error("no backward kernel for window %d", win); return MMIF_E_MODE;
+        }
+    } else if (zmode) {
+        if (fast) fusion_loss_bwd_kernel<11, true, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        else fusion_loss_bwd_kernel<11, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
     } else {
-        if (fast) fusion_loss_bwd_kernel<true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
-        else fusion_loss_bwd_kernel<false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        if (fast) fusion_loss_bwd_kernel<11, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        else fusion_loss_bwd_kernel<11, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
     }
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
@@ -510,7 +550,8 @@ extern "C" int mmif_fusion_loss_fwd(const float* i1, const float* i2, const floa
     }
     const size_t core = loss_ws_core_bytes(B, H, W);
     FwdLaunch L;
-    L.win = WIN; L.sigma = 1.5; L.epi = EPI_SSIM; L.finalize = FIN_LOSS; L.do_sobel = 1;
+    memset(&L, 0, sizeof(L));
+    L.win = WIN11; L.sigma = 1.5; L.epi = EPI_SSIM; L.finalize = FIN_LOSS; L.do_sobel = 1;
     L.data_range = cfg->data_range; L.cfg = *cfg;
     double* sums = (double*)((unsigned char*)ws + core);
     return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, out, ws, core, (cudaStream_t)stream);
@@ -544,6 +585,41 @@ extern "C" int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f
     cfg.w_ssim = 1.f; cfg.data_range = data_range;
     cfg.pixel_combine = cfg.grad_combine = MMIF_COMBINE_MAX; cfg.pixel_norm = cfg.grad_norm = MMIF_NORM_L1;
     BwdExtra ex;
+    memset(&ex, 0, sizeof(ex));
     ex.pair_w = pair_w; ex.ssim_base = scale; ex.cs_only = cs_only; ex.do_sobel = 0; ex.use_base = true;
+    return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
+}
+
+static double loss_sigma_of(int win) { return win == 11 ? 1.5 : 0.15 * (win - 1); }     // loss.py:34
+static bool msw_win_ok(int win) { return win == 11 || win == 9 || win == 7 || win == 5 || win == 3; }
+
+/* One window size of MSW_SSIM.forward (loss.py:226-237): out_sums[n] = sum over window positions of
+ * gamma*ssim(I1,If) + (1-gamma)*ssim(I2,If), gamma = sigma1/(sigma1+sigma2) per position (device doubles,
+ * B of them, stride 8).  Window sigma follows the loss rule (loss.py:34). */
+extern "C" int mmif_mswssim_fwd(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                                double* out_sums8, void* ws, size_t ws_bytes, void* stream) {
+    if (!i1 || !i2 || !f || !out_sums8) { set_error("null pointer"); return MMIF_E_NULL; }
+    if (!msw_win_ok(win)) { set_error("msw-ssim window %d unsupported (11, 9, 7, 5, 3)", win); return MMIF_E_MODE; }
+    FwdLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.win = win; L.sigma = loss_sigma_of(win); L.epi = EPI_MSW; L.finalize = FIN_SUMS; L.data_range = data_range;
+    L.cfg.pixel_norm = L.cfg.grad_norm = MMIF_NORM_L1;
+    return launch_moment_fwd(L, i1, i2, f, B, H, W, out_sums8, 8, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+/* Its backward: dF (+)= gout1[0] * scale * d(sum_n out_sums[n] / (Hout*Wout))/dIf. */
+extern "C" int mmif_mswssim_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                                const float* gout1, float scale, int accumulate, float* dF, void* ws, size_t ws_bytes, void* stream) {
+    if (!i1 || !i2 || !f || !gout1 || !dF) { set_error("null pointer"); return MMIF_E_NULL; }
+    if (!msw_win_ok(win)) { set_error("msw-ssim window %d unsupported (11, 9, 7, 5, 3)", win); return MMIF_E_MODE; }
+    if (B < 1 || H < win || W < win) { set_error("shape smaller than the window"); return MMIF_E_SHAPE; }
+    if (((uintptr_t)i1 | (uintptr_t)i2 | (uintptr_t)f | (uintptr_t)dF) & 3) { set_error("pointers must be 4-byte aligned"); return MMIF_E_ALIGN; }
+    MmifLossCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.w_ssim = 1.f; cfg.data_range = data_range;
+    cfg.pixel_combine = cfg.grad_combine = MMIF_COMBINE_MAX; cfg.pixel_norm = cfg.grad_norm = MMIF_NORM_L1;
+    BwdExtra ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.ssim_base = scale; ex.use_base = true; ex.win = win; ex.sigma = loss_sigma_of(win); ex.msw = 1; ex.accum = accumulate;
     return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
 }

@@ -81,6 +81,15 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
             case 3: return launch_t<3, EPI_VIF>(m1, m2, my, p, grid, st);
         }
     }
+    if (L.epi == EPI_MSW) {
+        switch (L.win) {
+            case 11: return launch_t<11, EPI_MSW>(m1, m2, my, p, grid, st);
+            case 9: return launch_t<9, EPI_MSW>(m1, m2, my, p, grid, st);
+            case 7: return launch_t<7, EPI_MSW>(m1, m2, my, p, grid, st);
+            case 5: return launch_t<5, EPI_MSW>(m1, m2, my, p, grid, st);
+            case 3: return launch_t<3, EPI_MSW>(m1, m2, my, p, grid, st);
+        }
+    }
     set_error("no kernel instantiated for window %d / epilogue %d", L.win, L.epi);
     return MMIF_E_MODE;
 }

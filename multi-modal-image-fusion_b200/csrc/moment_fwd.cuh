@@ -12,7 +12,7 @@
 
 namespace mmif {
 
-enum { EPI_SSIM = 0, EPI_VIF = 1 };
+enum { EPI_SSIM = 0, EPI_VIF = 1, EPI_MSW = 2 };
 enum { FIN_SUMS = 0, FIN_LOSS = 1 };
 
 // TMA needs the global address of a box (innermost coordinate * 4 B) 16-byte aligned, so strips
@@ -266,7 +266,16 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
                     const Stats st = stats_from(moments_of(acc[j]), sh);
                     const float2 vk = max2(st.vk, 0.f);
                     const float vy = fmaxf(st.vy, 0.f);
-                    if (EPI == EPI_SSIM) {
+                    if (EPI == EPI_MSW) {               // gamma-weighted SSIM of the two pairs (loss.py:230-235)
+                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
+                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
+                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
+                        const float2 B2 = add2(vk, bcast(vy + p.C2));
+                        const float2 S = fdiv_nr2(mul2(A1, A2), mul2(B1, B2));
+                        const float sg1 = fmaxf(vk.x, 1e-4f), sg2 = fmaxf(vk.y, 1e-4f);
+                        const float gm = __fdiv_rn(sg1, fmaxf(sg1 + sg2, 1e-7f));
+                        s0 = add2(s0, f2(gm * S.x + (1.f - gm) * S.y, 0.f));
+                    } else if (EPI == EPI_SSIM) {
                         const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
                         const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
                         const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));

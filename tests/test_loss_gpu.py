@@ -121,7 +121,7 @@ def test_errors_match_reference():
         ML.PixelLoss('l3')(x, x, x, mode='max')
     assert ML.PixelLoss('l1')(x, x, x, mode='other') is None
     with pytest.raises(NotImplementedError):
-        ML.SSIMLoss('msw-ssim')(x, x, x)
+        ML.SSIM(size_average=False)(x, x)
     with pytest.raises(Exception):
         ML.SSIMLoss('ssim')(x.cpu(), x.cpu(), x.cpu())   # no CPU fallback
 
@@ -242,3 +242,11 @@ def test_tv_loss_forward_backward(mode):
     gates.assert_scalar('tv', l.item(), OL.tv_loss(f - a, mode, 0.3).item(), l64.item())
     frac, mx, where = gates.grad_report(g.cpu().numpy(), g64.numpy())
     assert frac <= (1e-3 if mode == 'l1' else 0.0), (frac, mx, where)
+
+
+def test_msw_ssim_forward_backward():
+    ML = _mods()
+    for name in ('rand_3x64x96', 'rand_2x40x37'):
+        a, b, f = (T(x) for x in cases.loss_case(name))
+        _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('msw-ssim', weight=1.3)(x1, x2, y),
+                        lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'msw-ssim', weight=1.3), a, b, f)
