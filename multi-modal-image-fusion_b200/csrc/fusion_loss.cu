@@ -79,7 +79,9 @@ struct SmemBwd {
 // ZMODE: single-pass variant — the same launch also accumulates the three loss values (every window
 //        position / pixel is owned by exactly one CTA: the one whose gradient tile contains it), so
 //        forward + backward cost one kernel and 16 B/pixel instead of two kernels and 28 B/pixel.
-template <int WIN, bool FAST, bool ZMODE>
+// EXT  : the extended SSIM-only features (per-sample / per-position pair weights, cs-only, accumulate)
+//        used by 'w-ssim', MS-SSIM and MSW-SSIM; compiled out of the training-path instantiations.
+template <int WIN, bool FAST, bool ZMODE, bool EXT>
 __global__ void __launch_bounds__(kNT, 2)
 fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
@@ -119,7 +121,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
     const float npx = (float)p.B * (float)p.H * (float)p.W;
     const float k_ssim = g_ssim * p.ssim_base / ((float)p.Hout * (float)p.Wout);
-    const float2 pairw = p.pair_w ? f2(__ldg(p.pair_w + 2 * n), __ldg(p.pair_w + 2 * n + 1)) : f2(1.f, 1.f);
+    const float2 pairw = (EXT && p.pair_w) ? f2(__ldg(p.pair_w + 2 * n), __ldg(p.pair_w + 2 * n + 1)) : f2(1.f, 1.f);
     const float k_pix = g_pix * p.w_pixel / npx * (p.pixel_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
     const float k_grad = g_grad * p.w_grad / npx * (p.grad_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
 
@@ -137,7 +139,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
 #pragma unroll
     for (int d = 0; d < HALO; ++d) carry[d][0] = carry[d][1] = f2(0.f, 0.f);
 
-    if (!p.do_sobel) {
+    if (EXT || !p.do_sobel) {
         for (int i = t; i < kRB * (kTMC + 4); i += kNT) (&sb.gbuf[0][0])[i] = 0.f;     // B2 adds gbuf unconditionally
     }
     // Sobel-adjoint phase: column of this thread and its sliding state
@@ -164,7 +166,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         // thread = column (warps own 30 columns + 1 halo lane each side); one input row per step:
         // input row q' -> Sobel / tx,ty of row q'-1 -> (neighbour columns by shuffle) -> G of row q'-2.
         // All sliding state lives in registers across batches, so every input row is visited once.
-        if (p.do_sobel) {
+        if (!EXT && p.do_sobel) {
 #pragma unroll 2
             for (int step = 0; step < kRB; ++step) {
                 const int qp = Rb + 2 + step;                       // input row q'
@@ -251,7 +253,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                         const float2 rB2 = fdiv_nr2(bcast(1.f), B2);
                         const float2 rBB = mul2(rB1, rB2);
                         float2 S, dcov, dvar, dmu;
-                        if (p.cs_only) {                                                 // S = cs = A2 / B2
+                        if (EXT && p.cs_only) {                                          // S = cs = A2 / B2
                             S = mul2(A2, rB2);
                             dcov = muls(2.f, rB2);
                             dvar = muls(-myk, mul2(S, rB2));
@@ -267,13 +269,18 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                         const float2 a = fma2(muls(-1.f, dcov), add2(mo.mk, sh.ec),
                                               fma2(muls(-1.f, dvar), bcast(2.f * mo.my + sh.k1y), dmu));
                         float2 wq = pairw;
-                        if (p.msw) {                                                     // gamma = sigma1 / (sigma1 + sigma2), loss.py:232-233
+                        if (EXT && p.msw) {                                                     // gamma = sigma1 / (sigma1 + sigma2), loss.py:232-233
                             const float sg1 = fmaxf(vk.x, 1e-4f), sg2 = fmaxf(vk.y, 1e-4f);
                             const float gm = __fdiv_rn(sg1, fmaxf(sg1 + sg2, 1e-7f));
                             wq = f2(gm, 1.f - gm);
                         }
-                        ab[j] = f2(wq.x * a.x + wq.y * a.y, wq.x * dvar.x + wq.y * dvar.y);
-                        cc[j] = mul2(dcov, wq);
+                        if (EXT) {
+                            ab[j] = f2(wq.x * a.x + wq.y * a.y, wq.x * dvar.x + wq.y * dvar.y);
+                            cc[j] = mul2(dcov, wq);
+                        } else {
+                            ab[j] = f2(a.x + a.y, dvar.x + dvar.y);
+                            cc[j] = dcov;
+                        }
                         if (ZMODE && q >= i0 && q < iend && pc >= j0 && pc < jend) {
                             z_ss = add2(z_ss, S);
                             z_cs = add2(z_cs, mul2(A2, rB2));
@@ -356,7 +363,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                     outv[j] = fmaf(k_ssim, dS, gb[j]);
                 }
                 float* dst = p.dF + img_off + (size_t)i * p.W + j0 + hg * 8;
-                if (p.accum) {
+                if (EXT && p.accum) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         if (j0 + hg * 8 + j < jend) outv[j] += dst[j];
@@ -494,14 +501,16 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     static bool attr_done = false;
     if (!attr_done) {
         const int sz = (int)sizeof(SmemBwd);
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<9, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<7, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+        const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, false, false>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, false, false>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, true, false>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, true, false>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, false, false, true>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<9, false, false, true>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<7, false, false, true>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false, true>, at, sz));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false, true>, at, sz));
         attr_done = true;
     }
     dim3 grid(g.nstrip, g.nseg, B);
@@ -512,23 +521,24 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaGetLastError());
     }
     const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
-                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1 && p.do_sobel;
+                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
     const size_t sm = sizeof(SmemBwd);
-    if (win != 11) {
-        if (zmode || p.do_sobel) { set_error("window %d: only the SSIM-only backward is instantiated", win); return MMIF_E_MODE; }
+    if (ex) {                         // SSIM-only extended launches ('w-ssim', MS-SSIM levels, MSW-SSIM windows)
+        if (zmode || p.do_sobel) { set_error("extended backward is SSIM-only"); return MMIF_E_MODE; }
         switch (win) {
-            case 9: fusion_loss_bwd_kernel<9, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
-            case 7: fusion_loss_bwd_kernel<7, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
-            case 5: fusion_loss_bwd_kernel<5, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
-            case 3: fusion_loss_bwd_kernel<3, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 11: fusion_loss_bwd_kernel<11, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 9: fusion_loss_bwd_kernel<9, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 7: fusion_loss_bwd_kernel<7, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 5: fusion_loss_bwd_kernel<5, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
+            case 3: fusion_loss_bwd_kernel<3, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
             default: set_error("no backward kernel for window %d", win); return MMIF_E_MODE;
         }
     } else if (zmode) {
-        if (fast) fusion_loss_bwd_kernel<11, true, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
-        else fusion_loss_bwd_kernel<11, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        if (fast) fusion_loss_bwd_kernel<11, true, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        else fusion_loss_bwd_kernel<11, false, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
     } else {
-        if (fast) fusion_loss_bwd_kernel<11, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
-        else fusion_loss_bwd_kernel<11, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        if (fast) fusion_loss_bwd_kernel<11, true, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
+        else fusion_loss_bwd_kernel<11, false, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
     }
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
