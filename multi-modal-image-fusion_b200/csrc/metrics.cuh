@@ -4,7 +4,7 @@
 
 namespace mmif {
 
-constexpr int kQabfRows = 32;      // rows per Qabf CTA
+constexpr int kPixelMinRows = 8;  // smallest row chunk of a stats / Qabf CTA (workspace sizing)
 constexpr int kRawPerPair = 160;   // doubles of raw per-pair results inside the workspace
 
 // Workspace carve-up (all device memory owned by the caller, see mmif_metric_workspace_bytes).
@@ -13,7 +13,7 @@ struct MetricWs {
     double* partial;        // per-CTA partial sums of the simple kernels
     unsigned char* fwd_ws;  // counters + partials of the strip-streaming kernel
     size_t fwd_ws_bytes;
-    uint32_t* hist_extra;   // [N][768], zero between launches
+    uint32_t* hist_extra;   // [hist_extra_words(N)], zero between launches
     double* raw;            // [N][kRawPerPair]
     float* pyr;             // pyramid levels (MS-SSIM) / decimated scales (VIF)
     size_t pyr_floats;
@@ -41,8 +41,11 @@ int launch_hist(const float* a, const float* b, const float* f, int N, int H, in
                 long long estride, MetricWs& ws, cudaStream_t st);
 int launch_qabf(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out, long long ostride,
                 MetricWs& ws, cudaStream_t st);
+int launch_pixel_metrics(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out_s,
+                         long long sstride, double* out_q, long long qstride, MetricWs& ws, cudaStream_t st);
 int launch_tv(const float* x, int N, int H, int W, int norm, float weight, double* out, MetricWs& ws, cudaStream_t st);
 int stats_rows_per_block(int N, int H);
+size_t hist_extra_words(int N);
 
 #ifdef __CUDACC__
 // Block partial -> global; the last block of sample n re-reduces all partials of that sample in a

@@ -104,40 +104,63 @@ __global__ void __launch_bounds__(256) halve_kernel(Ptr3 p, int N, int H, int W,
     p.dst[k][((size_t)n * Ho + i) * Wo + j] = (((a + b) + c) + d) * 0.25f;
 }
 
-// VIF scale step (metric.py:419-423): valid k x k Gaussian blur, then every other row / column.
-// Tile of 32 x 16 outputs per CTA: the (64+k-1) x (32+k-1) input patch is staged in shared memory,
-// blurred horizontally at the even columns, then vertically at the even rows (separable: 3k FMA per
-// output instead of k^2).
-constexpr int kBdTx = 32, kBdTy = 16, kBdMaxK = 9;
-__global__ void __launch_bounds__(256) blur_decimate_kernel(Ptr3 p, int N, int H, int W, int Ho, int Wo, int k, const Taps taps) {
-    __shared__ float tin[2 * kBdTy + kBdMaxK - 1][2 * kBdTx + kBdMaxK - 1 + 1];
-    __shared__ float tmid[2 * kBdTy + kBdMaxK - 1][kBdTx + 1];
-    const int im = blockIdx.z % 3, n = blockIdx.z / 3;
-    const float* s = p.src[im] + (size_t)n * H * W;
-    const int oj0 = blockIdx.x * kBdTx, oi0 = blockIdx.y * kBdTy;
-    const int rows_in = 2 * kBdTy + k - 1, cols_in = 2 * kBdTx + k - 1;
-    const int r0 = 2 * oi0, c0 = 2 * oj0;
-    for (int idx = threadIdx.x; idx < rows_in * cols_in; idx += 256) {
-        const int r = idx / cols_in, c = idx % cols_in;
-        const int gr = r0 + r, gc = c0 + c;
-        tin[r][c] = (gr < H && gc < W) ? __ldg(s + (size_t)gr * W + gc) : 0.f;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < rows_in * kBdTx; idx += 256) {
-        const int r = idx / kBdTx, j = idx % kBdTx;
-        float acc = 0.f;
-        for (int v = 0; v < k; ++v) acc = fmaf(taps.w[v], tin[r][2 * j + v], acc);
-        tmid[r][j] = acc;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < kBdTy * kBdTx; idx += 256) {
-        const int i = idx / kBdTx, j = idx % kBdTx;
-        if (oi0 + i < Ho && oj0 + j < Wo) {
-            float acc = 0.f;
-            for (int u = 0; u < k; ++u) acc = fmaf(taps.w[u], tmid[2 * i + u][j], acc);
-            p.dst[im][((size_t)n * Ho + oi0 + i) * Wo + oj0 + j] = acc;
+// VIF scale step (metric.py:419-423): valid K x K Gaussian blur, then every other row / column.
+// thread = output column, marching down a segment of output rows: each input row is blurred
+// horizontally at the even columns straight from global memory (K contiguous values per thread, 8-byte
+// loads when the pitch allows; a warp covers 64+K-1 contiguous floats per row, the re-reads hit L1), the
+// last K horizontal results slide through registers and every second row emits one vertical blur:
+// 3K/4 FMA per input pixel, each input read from DRAM once.
+constexpr int kBdRows = 32;      // output rows per CTA
+template <int K, bool VEC>
+__device__ __forceinline__ float hblur_row(const float* __restrict__ q, const Taps& taps) {
+    float acc = 0.f;
+    if (VEC) {
+#pragma unroll
+        for (int v = 0; v + 1 < K; v += 2) {
+            const float2 x = __ldg(reinterpret_cast<const float2*>(q + v));
+            acc = fmaf(taps.w[v], x.x, acc);
+            acc = fmaf(taps.w[v + 1], x.y, acc);
         }
+        acc = fmaf(taps.w[K - 1], __ldg(q + K - 1), acc);      // K is odd
+    } else {
+#pragma unroll
+        for (int v = 0; v < K; ++v) acc = fmaf(taps.w[v], __ldg(q + v), acc);
     }
+    return acc;
+}
+template <int K, bool VEC>
+__global__ void __launch_bounds__(128) blur_decimate_kernel(Ptr3 p, int N, int H, int W, int Ho, int Wo, const __grid_constant__ Taps taps) {
+    const int im = blockIdx.z % 3, n = blockIdx.z / 3;
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (j >= Wo) return;
+    const int oi0 = blockIdx.y * kBdRows, oi1 = min(oi0 + kBdRows, Ho);
+    const float* q = p.src[im] + (size_t)n * H * W + (size_t)(2 * oi0) * W + 2 * j;
+    float* dst = p.dst[im] + ((size_t)n * Ho + oi0) * Wo + j;
+    float h[K];                                  // horizontal blurs of input rows 2*oi .. 2*oi + K-1
+#pragma unroll
+    for (int u = 0; u < K - 2; ++u) h[u + 2] = hblur_row<K, VEC>(q + (size_t)u * W, taps);
+    q += (size_t)(K - 2) * W;
+    for (int oi = oi0; oi < oi1; ++oi) {
+#pragma unroll
+        for (int u = 0; u < K - 2; ++u) h[u] = h[u + 2];
+        h[K - 2] = hblur_row<K, VEC>(q, taps);
+        h[K - 1] = hblur_row<K, VEC>(q + W, taps);
+        q += 2 * (size_t)W;
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < K; ++u) acc = fmaf(taps.w[u], h[u], acc);
+        *dst = acc;
+        dst += Wo;
+    }
+}
+template <int K>
+static int launch_bd(const Ptr3& p, int N, int H, int W, int Ho, int Wo, const Taps& taps, cudaStream_t st) {
+    dim3 grid(ceil_div(Wo, 128), ceil_div(Ho, kBdRows), 3 * N);
+    const bool vec = ((W & 1) == 0) && ((((uintptr_t)p.src[0] | (uintptr_t)p.src[1] | (uintptr_t)p.src[2]) & 7) == 0);
+    if (vec) blur_decimate_kernel<K, true><<<grid, 128, 0, st>>>(p, N, H, W, Ho, Wo, taps);
+    else blur_decimate_kernel<K, false><<<grid, 128, 0, st>>>(p, N, H, W, Ho, Wo, taps);
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
 }
 
 // =============================================================================== compose kernels
@@ -256,7 +279,7 @@ static size_t vif_pyr_floats(int N, int H, int W) {
 size_t metric_ws_bytes(int N, int H, int W) {
     if (N < 1 || H < 1 || W < 1) return 0;
     size_t partial = (size_t)N * ceil_div(H, stats_rows_per_block(N, H)) * 14;
-    const size_t pq = (size_t)N * ceil_div(W, 128) * ceil_div(H, kQabfRows) * 5;
+    const size_t pq = (size_t)N * ceil_div(W, 128) * ceil_div(H, kPixelMinRows) * 19;
     const size_t ps = (size_t)N * (((size_t)H * W + 255) / 256) * 8;
     partial = partial > pq ? partial : pq;
     partial = partial > ps ? partial : ps;
@@ -267,7 +290,7 @@ size_t metric_ws_bytes(int N, int H, int W) {
     for (int s = 0; s < 4; ++s) { const size_t b = fwd_ws_bytes(kVifWin[s], N, vd.h[s], vd.w[s]); fwd = fwd > b ? fwd : b; }
     const size_t pm = msssim_pyr_floats(N, H, W), pv = vif_pyr_floats(N, H, W);
     const size_t pyr = pm > pv ? pm : pv;
-    return al256((size_t)(N + 1) * 4) + al256(partial * 8) + al256(fwd) + al256((size_t)N * 768 * 4) +
+    return al256((size_t)(N + 1) * 4) + al256(partial * 8) + al256(fwd) + al256(hist_extra_words(N) * 4) +
            al256((size_t)N * kRawPerPair * 8) + al256(pyr * 4) + al256((size_t)N * MMIF_HIST_WORDS * 4) + 256;
 }
 
@@ -277,7 +300,7 @@ int carve_metric_ws(MetricWs* w, void* ws, size_t ws_bytes, int N, int H, int W)
     if (((uintptr_t)ws) & 255) { set_error("metric workspace must be 256-byte aligned"); return MMIF_E_ALIGN; }
     unsigned char* p = (unsigned char*)ws;
     size_t partial = (size_t)N * ceil_div(H, stats_rows_per_block(N, H)) * 14;
-    const size_t pq = (size_t)N * ceil_div(W, 128) * ceil_div(H, kQabfRows) * 5;
+    const size_t pq = (size_t)N * ceil_div(W, 128) * ceil_div(H, kPixelMinRows) * 19;
     const size_t ps = (size_t)N * (((size_t)H * W + 255) / 256) * 8;
     partial = partial > pq ? partial : pq;
     partial = partial > ps ? partial : ps;
@@ -290,7 +313,7 @@ int carve_metric_ws(MetricWs* w, void* ws, size_t ws_bytes, int N, int H, int W)
     w->counters = (unsigned*)p; p += al256((size_t)(N + 1) * 4);
     w->partial = (double*)p; p += al256(partial * 8);
     w->fwd_ws = p; w->fwd_ws_bytes = al256(fwd); p += al256(fwd);
-    w->hist_extra = (uint32_t*)p; p += al256((size_t)N * 768 * 4);
+    w->hist_extra = (uint32_t*)p; p += al256(hist_extra_words(N) * 4);
     w->raw = (double*)p; p += al256((size_t)N * kRawPerPair * 8);
     w->pyr = (float*)p; w->pyr_floats = pm > pv ? pm : pv; p += al256(w->pyr_floats * 4);
     w->counts = (uint32_t*)p;
@@ -337,9 +360,11 @@ static int run_vif(const float* a, const float* b, const float* f, int N, int H,
             const size_t per = (size_t)N * ho * wo;
             p.src[0] = ca; p.src[1] = cb; p.src[2] = cf;
             p.dst[0] = base; p.dst[1] = base + per; p.dst[2] = base + 2 * per;
-            dim3 grid(ceil_div(wo, kBdTx), ceil_div(ho, kBdTy), 3 * N);
-            blur_decimate_kernel<<<grid, 256, 0, st>>>(p, N, d.h[s - 1], d.w[s - 1], ho, wo, k, taps);
-            MMIF_CUDA(cudaGetLastError());
+            int rc = MMIF_OK;
+            if (k == 9) rc = launch_bd<9>(p, N, d.h[s - 1], d.w[s - 1], ho, wo, taps, st);
+            else if (k == 5) rc = launch_bd<5>(p, N, d.h[s - 1], d.w[s - 1], ho, wo, taps, st);
+            else rc = launch_bd<3>(p, N, d.h[s - 1], d.w[s - 1], ho, wo, taps, st);
+            if (rc) return rc;
             ca = p.dst[0]; cb = p.dst[1]; cf = p.dst[2];
             base += 3 * per;
         }
@@ -438,10 +463,9 @@ extern "C" int mmif_eval_suite(const float* a, const float* b, const float* f, i
     if (H < 11 || W < 11) { set_error("eval suite needs H,W >= 11"); return MMIF_E_SHAPE; }
     MetricWs w; rc = carve_metric_ws(&w, ws, ws_bytes, N, H, W); if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_stats(a, b, f, N, H, W, w.raw + RAW_STATS, kRawPerPair, w, st); if (rc) return rc;
+    rc = launch_pixel_metrics(a, b, f, N, H, W, 1.5f, w.raw + RAW_STATS, kRawPerPair, w.raw + RAW_QABF, kRawPerPair, w, st); if (rc) return rc;
     MMIF_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)N * MMIF_HIST_WORDS * 4, st));
     rc = launch_hist(a, b, f, N, H, W, w.counts, w.raw + RAW_ENT, kRawPerPair, w, st); if (rc) return rc;
-    rc = launch_qabf(a, b, f, N, H, W, 1.5f, w.raw + RAW_QABF, kRawPerPair, w, st); if (rc) return rc;
     // level 0 of the MS-SSIM pyramid is calc_ssim(.., data_range=255) itself (metric.py:379-384)
     rc = run_msssim(a, b, f, N, H, W, 11, 255.f, w.raw + RAW_MS, kRawPerPair, w, st); if (rc) return rc;
     rc = run_vif(a, b, f, N, H, W, w.raw + RAW_VIF, kRawPerPair, w, st); if (rc) return rc;

@@ -147,3 +147,35 @@ def test_constant_images_and_errors():
         assert np.isnan(row[nm]) == np.isnan(r32[nm]), (nm, row[nm], r32[nm])
     with pytest.raises(Exception):
         MM.calc_viff(torch.rand(1, 1, 20, 20).cuda(), torch.rand(1, 1, 20, 20).cuda(), torch.rand(1, 1, 20, 20).cuda())
+
+
+@pytest.mark.parametrize('n_pairs', [1, 16])
+def test_histogram_counter_overflow_and_split_modes(n_pairs):
+    """Bins far above the 15-bit shared-memory counters (flat / two-valued images), in the split mode
+    (few pairs: several CTAs add into one global histogram) and in the fused mode (>= 16 pairs: one CTA
+    per joint finishes from shared memory); entropies against the live oracle."""
+    MM = _mods()
+    g = torch.Generator().manual_seed(5)
+    H, W = 300, 400
+    a = torch.full((n_pairs, 1, H, W), 255.0)
+    a[:, :, :, 100:] = torch.randint(0, 2, (n_pairs, 1, H, W - 100), generator=g).float() * 7.0
+    b = torch.full((n_pairs, 1, H, W), 256.0)                  # lands in bin 255
+    b[:, :, 17, :] = -1.0                                       # dropped samples: marginal of f only
+    f = torch.full((n_pairs, 1, H, W), 3.0)
+    f[:, :, :50, :] = torch.randint(0, 256, (n_pairs, 1, 50, W), generator=g).float()
+    counts, ent = MM._hist(a.cuda(), b.cuda(), f.cuda(), want_counts=True)
+    counts = counts.to(torch.int64).cpu().numpy()
+    ent = ent.cpu().numpy()
+    for n in range(n_pairs):
+        an, bn, fn = a[n:n + 1], b[n:n + 1], f[n:n + 1]
+        assert np.array_equal(counts[n, 0:256], OM.hist_counts(an).to(torch.int64).numpy())
+        assert np.array_equal(counts[n, 256:512], OM.hist_counts(bn).to(torch.int64).numpy())
+        assert np.array_equal(counts[n, 512:768], OM.hist_counts(fn).to(torch.int64).numpy())
+        assert np.array_equal(counts[n, 768:768 + 65536].reshape(256, 256), OM.joint_counts(an, fn).numpy().astype(np.int64))
+        assert np.array_equal(counts[n, 768 + 65536:].reshape(256, 256), OM.joint_counts(bn, fn).numpy().astype(np.int64))
+        for k, (x, y) in enumerate(((an, fn), (bn, fn))):
+            r32 = OM.mutual_info(x, y, normalized=True).item()
+            r64 = OM.mutual_info(x.double(), y.double(), normalized=True).item()
+            gates.assert_scalar(f'ovf/nmi{k}', ent[n, 9 + k], r32, r64)
+            gates.assert_scalar(f'ovf/ce{k}', ent[n, 5 + k], OM.cross_entropy(x, y).item(), OM.cross_entropy(x.double(), y.double()).item())
+        gates.assert_scalar('ovf/en_f', ent[n, 2], OM.entropy(fn).item(), OM.entropy(fn.double()).item())
