@@ -104,6 +104,39 @@ __global__ void __launch_bounds__(256) halve_kernel(Ptr3 p, int N, int H, int W,
     p.dst[k][((size_t)n * Ho + i) * Wo + j] = (((a + b) + c) + d) * 0.25f;
 }
 
+// Same step when the row pitch allows 16-byte loads (W % 4 == 0, so no odd-column pad): one thread =
+// 2 x 2 outputs from four float4 loads (64 B in flight per thread), the odd bottom row reflected.
+__global__ void __launch_bounds__(256) halve4_kernel(Ptr3 p, int N, int H, int W, int Ho, int Wo) {
+    const int k = blockIdx.z % 3, n = blockIdx.z / 3;
+    const int j2 = blockIdx.x * 32 + (threadIdx.x & 31);          // pair of output columns
+    const int i2 = blockIdx.y * 8 + (threadIdx.x >> 5);           // pair of output rows
+    if (2 * j2 >= Wo || 2 * i2 >= Ho) return;
+    const float* s = p.src[k] + (size_t)n * H * W + 4 * j2;
+    float* d = p.dst[k] + ((size_t)n * Ho + 2 * i2) * Wo + 2 * j2;
+    const int r0 = 4 * i2;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(s + (size_t)r0 * W));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(s + (size_t)((r0 + 1 < H) ? r0 + 1 : H - 2) * W));
+    *reinterpret_cast<float2*>(d) = make_float2((((a0.x + a0.y) + a1.x) + a1.y) * 0.25f, (((a0.z + a0.w) + a1.z) + a1.w) * 0.25f);
+    if (2 * i2 + 1 < Ho) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(s + (size_t)(r0 + 2) * W));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(s + (size_t)((r0 + 3 < H) ? r0 + 3 : H - 2) * W));
+        *reinterpret_cast<float2*>(d + Wo) = make_float2((((b0.x + b0.y) + b1.x) + b1.y) * 0.25f, (((b0.z + b0.w) + b1.z) + b1.w) * 0.25f);
+    }
+}
+static int launch_halve(const Ptr3& p, int N, int H, int W, int Ho, int Wo, cudaStream_t st) {
+    bool vec = (W % 4 == 0);
+    for (int k = 0; k < 3; ++k) vec = vec && ((((uintptr_t)p.src[k]) & 15) == 0) && ((((uintptr_t)p.dst[k]) & 7) == 0);
+    if (vec) {
+        dim3 grid(ceil_div(Wo, 64), ceil_div(Ho, 16), 3 * N);
+        halve4_kernel<<<grid, 256, 0, st>>>(p, N, H, W, Ho, Wo);
+    } else {
+        dim3 grid(ceil_div(Wo, 64), ceil_div(Ho, 4), 3 * N);
+        halve_kernel<<<grid, 256, 0, st>>>(p, N, H, W, Ho, Wo);
+    }
+    MMIF_CUDA(cudaGetLastError());
+    return MMIF_OK;
+}
+
 // VIF scale step (metric.py:419-423): valid K x K Gaussian blur, then every other row / column.
 // thread = output column, marching down a segment of output rows: each input row is blurred
 // horizontally at the even columns straight from global memory (K contiguous values per thread, 8-byte
@@ -335,9 +368,7 @@ static int run_msssim(const float* a, const float* b, const float* f, int N, int
         const size_t per = (size_t)N * ho * wo;
         p.src[0] = ca; p.src[1] = cb; p.src[2] = cf;
         p.dst[0] = base; p.dst[1] = base + per; p.dst[2] = base + 2 * per;
-        dim3 grid(ceil_div(wo, 64), ceil_div(ho, 4), 3 * N);
-        halve_kernel<<<grid, 256, 0, st>>>(p, N, d.h[l], d.w[l], ho, wo);
-        MMIF_CUDA(cudaGetLastError());
+        { const int rc2 = launch_halve(p, N, d.h[l], d.w[l], ho, wo, st); if (rc2) return rc2; }
         ca = p.dst[0]; cb = p.dst[1]; cf = p.dst[2];
         base += 3 * per;
     }

@@ -20,13 +20,14 @@ constexpr int kStatK = 14;
 constexpr int kQK = 5;
 
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // atan2(y, x) in (-pi, pi]: |error| < 1.5e-7 (degree-8 minimax in (min/max)^2, fp32 Horner); atan2(+0, +0) = 0,
 // atan2(+0, x < 0) = pi like the reference's torch.atan2 (the Sobel differences of a flat patch are +0).
 __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = (mx > 0.f) ? fdiv_nr(mn, mx) : 0.f;
+    const float a = (mx > 0.f) ? mn * rcp_fast(mx) : 0.f;       // 1-ulp reciprocal: |d atan| <= 1.2e-7
     const float s = a * a;
     float p = 0.002456702059134841f;
     p = fmaf(p, s, -0.014401260763406754f);
@@ -45,7 +46,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 // gamma / (1 + exp(-k (v - sigma)))   (metric.py:224-225)
 __device__ __forceinline__ float sigmoid_q(float gamma, float k, float sigma, float v) {
     const float e = ex2_fast(-k * 1.4426950408889634f * (v - sigma));
-    return fdiv_nr(gamma, 1.f + e);
+    return gamma * rcp_fast(1.f + e);
 }
 
 template <bool STATS, bool QABF>
@@ -106,7 +107,7 @@ pixel_metrics_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
                 const float dx = pfr - ff, dy = uc[2] - ff;
                 if (hasx) s[10] = fmaf(dx, dx, s[10]);
                 if (hasy) s[11] = fmaf(dy, dy, s[11]);
-                if (hasx && hasy) s[9] += sqrtf((dx * dx + dy * dy) * 0.5f);     // metric.py:44
+                if (hasx && hasy) s[9] += sqrt_fast((dx * dx + dy * dy) * 0.5f);  // metric.py:44
                 const float ea = fa - ff, eb = fb - ff;
                 s[12] = fmaf(ea, ea, s[12]); s[13] = fmaf(eb, eb, s[13]);
             }
@@ -118,7 +119,7 @@ pixel_metrics_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const float mx = fmaxf(g[k], g[2]), mn = fminf(g[k], g[2]);
-                    const float G = (mx > 0.f) ? fdiv_nr(mn, mx) : 0.f;                  // 0/0 -> 0, metric.py:213-215
+                    const float G = (mx > 0.f) ? mn * rcp_fast(mx) : 0.f;                // 0/0 -> 0, metric.py:213-215
                     const float Aa = fabsf(fabsf(al[k] - al[2]) - 1.5707963267948966f) * 0.6366197723675814f;
                     Q[k] = sigmoid_q(0.9994f, 15.f, 0.5f, G) * sigmoid_q(0.9879f, 22.f, 0.8f, Aa);   // metric.py:218-225
                     w[k] = (Lexp == 1.5f) ? g[k] * sqrt_fast(g[k]) : powf(g[k], Lexp);     // eval.py:45 uses L=1.5
@@ -226,22 +227,25 @@ struct HistSmem {
     int flag;
 };
 
+__device__ __forceinline__ void hist_add(HistSmem& sm, uint32_t* gj, uint32_t idx) {
+    const uint32_t delta = 1u << ((idx & 1u) << 4);
+    const uint32_t old = atomicAdd(&sm.jh[idx >> 1], delta);
+    if (((old + delta) & ~old) & (delta << 15)) {          // this increment set the guard bit of its counter
+        atomicSub(&sm.jh[idx >> 1], delta << 15);
+        atomicAdd(&gj[idx], 0x8000u);
+    }
+}
 __device__ __forceinline__ void hist_count(HistSmem& sm, uint32_t* gj, float vs, float vf) {
+    // fast path: floor(v) + 2^23 by a round-down add; 0 <= v < 256 <=> the biased bits are <= 255
+    const uint32_t us = __float_as_uint(__fadd_rd(vs, 8388608.f)) - 0x4B000000u;
+    const uint32_t uf = __float_as_uint(__fadd_rd(vf, 8388608.f)) - 0x4B000000u;
+    if (max(us, uf) <= 255u) { hist_add(sm, gj, us * 256u + uf); return; }
+    // rare: a value of exactly 256 (bin 255) or a sample to drop
     const bool oks = (vs >= 0.f) && (vs <= 256.f), okf = (vf >= 0.f) && (vf <= 256.f);
     const int bs = min(__float2int_rz(vs), 255), bf = min(__float2int_rz(vf), 255);
-    if (oks && okf) {
-        const int idx = bs * 256 + bf;
-        const uint32_t sh = (idx & 1) * 16;
-        const uint32_t old = atomicAdd(&sm.jh[idx >> 1], 1u << sh);
-        if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {          // this increment set the guard bit
-            atomicSub(&sm.jh[idx >> 1], 0x8000u << sh);
-            atomicAdd(&gj[idx], 0x8000u);
-        }
-    } else if (oks) {
-        atomicAdd(&sm.exs[bs], 1u);                        // source counted in its marginal only
-    } else if (okf) {
-        atomicAdd(&sm.exf[bf], 1u);                        // f counted in its marginal only
-    }
+    if (oks && okf) hist_add(sm, gj, (uint32_t)(bs * 256 + bf));
+    else if (oks) atomicAdd(&sm.exs[bs], 1u);                  // source counted in its marginal only
+    else if (okf) atomicAdd(&sm.exf[bf], 1u);                  // f counted in its marginal only
 }
 
 __global__ void __launch_bounds__(kHT, 1)

@@ -196,9 +196,23 @@ __device__ __forceinline__ void fwd_sobel_pixel_fast(const SM& sm, int H, int W,
     }
 }
 
-// log2(1+x), accurate for small x (the reference's fp32 log2(1 + x) loses x's low bits; its fp64
-// evaluation does not — stay near the fp64 value).
-__device__ __forceinline__ float log2_1p(float x) { return log1pf(x) * 1.4426950408889634f; }
+// VIF sums of log2(1 + x) (metric.py:454-456) are kept as running PRODUCTS of (1 + x) in double
+// (mantissa in [1,2) + an integer exponent, renormalised once per batch of 8 factors): the FP64 pipe is
+// idle in this kernel, the FP32 pipe is its bottleneck, and a logarithm is taken once per thread at
+// the end instead of four times per pixel.  Exact to double rounding, i.e. nearer the reference's
+// fp64 evaluation than its fp32 log2(1 + x), which loses the low bits of a small x.
+struct LogProd {
+    double m; int e;
+    __device__ __forceinline__ void init() { m = 1.0; e = 0; }
+    __device__ __forceinline__ void mul(double f) { m *= f; }
+    __device__ __forceinline__ void renorm() {          // m >= 1 always (factors are >= 1)
+        int hi = __double2hiint(m);
+        const int lo = __double2loint(m);
+        const int ex = (hi >> 20) - 1023;
+        if (ex < 1024) { e += ex; hi -= ex << 20; m = __hiloint2double(hi, lo); }     // inf / nan stay as they are
+    }
+    __device__ __forceinline__ double log2_total() const { return (double)e + log2(m); }
+};
 
 template <int WIN, int EPI>
 __global__ void __launch_bounds__(kNT, 3)
@@ -238,6 +252,9 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
     const int ho = lane & 7, hg = warp * 4 + (lane >> 3);
     float2 s0 = f2(0.f, 0.f), s1 = f2(0.f, 0.f), s2 = f2(0.f, 0.f);   // three packed running sums
     float pix_sum = 0.f, grad_sum = 0.f;
+    LogProd lp[6];                                                     // EPI_VIF: num1, den1, num2, den2, numsel, densel
+#pragma unroll
+    for (int i = 0; i < 6; ++i) lp[i].init();
     const int clo = (strip == 0) ? 0 : j0 + HALO / 2;
     const int chi = (strip == p.nstrip - 1) ? p.W : j0 + TWO + HALO / 2;
     constexpr float kVifEps = 1e-10f, kVifNoise = 325.125f;            // metric.py:407-408
@@ -284,27 +301,31 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
                         s1 = add2(s1, fdiv_nr2(A2, B2));
                         s2 = add2(s2, max2(vk, 1e-4f));
                     } else {
-                        float num[2], den[2], gg[2];
+                        double fn[2], fd[2];
+                        float gg[2];
                         const float v1[2] = {vk.x, vk.y}, c12[2] = {st.cov.x, st.cov.y};
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             float sig1 = v1[k];
-                            float g = __fdiv_rn(c12[k], sig1 + kVifEps);
+                            float g = fdiv_nr(c12[k], sig1 + kVifEps);
                             float sv = vy - g * c12[k];
                             if (sig1 < kVifEps) { g = 0.f; sv = vy; sig1 = 0.f; }
                             if (vy < kVifEps) { g = 0.f; sv = 0.f; }
                             if (g < 0.f) { sv = vy; g = 0.f; }
                             if (sv < kVifEps) sv = kVifEps;
-                            num[k] = log2_1p(__fdiv_rn(g * g * sig1, sv + kVifNoise));
-                            den[k] = log2_1p(sig1 * (1.0f / kVifNoise));
+                            fn[k] = 1.0 + (double)fdiv_nr(g * g * sig1, sv + kVifNoise);
+                            fd[k] = 1.0 + (double)(sig1 * (1.0f / kVifNoise));
                             gg[k] = g;
                         }
                         const bool pick1 = gg[0] < gg[1];
-                        s0 = add2(s0, f2(num[0], den[0]));
-                        s1 = add2(s1, f2(num[1], den[1]));
-                        s2 = add2(s2, pick1 ? f2(num[0], den[0]) : f2(num[1], den[1]));
+                        lp[0].mul(fn[0]); lp[1].mul(fd[0]); lp[2].mul(fn[1]); lp[3].mul(fd[1]);
+                        lp[4].mul(pick1 ? fn[0] : fn[1]); lp[5].mul(pick1 ? fd[0] : fd[1]);
                     }
                 }
+            }
+            if (EPI == EPI_VIF) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) lp[i].renorm();
             }
         }
         __syncthreads();
@@ -314,6 +335,10 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
     // SSIM: [ssim1, ssim2, cs1, cs2, sig1, sig2, pix, grad]; VIF: [num1, den1, num2, den2, numsel, densel, 0, 0]
     double v[8] = {(double)s0.x, (double)s0.y, (double)s1.x, (double)s1.y, (double)s2.x, (double)s2.y,
                    (double)pix_sum, (double)grad_sum};
+    if (EPI == EPI_VIF) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = lp[i].log2_total();
+    }
     cta_finish<kNT>(p.fin, v, sm.red, &sm.flag, n, seg * p.nstrip + strip, p.nstrip * p.nseg);
 }
 
