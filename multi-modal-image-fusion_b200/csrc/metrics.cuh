@@ -18,6 +18,8 @@ struct MetricWs {
     float* pyr;             // pyramid levels (MS-SSIM) / decimated scales (VIF)
     size_t pyr_floats;
     uint32_t* counts;       // [N][MMIF_HIST_WORDS] histogram block used by mmif_eval_suite
+    unsigned char* fwd_ws_b; // second strip-kernel workspace + pyramid: the VIF chain of mmif_eval_suite runs
+    float* pyr_b;            // concurrently with the MS-SSIM chain (forked streams)
 };
 size_t metric_ws_bytes(int N, int H, int W);
 int carve_metric_ws(MetricWs* w, void* ws, size_t ws_bytes, int N, int H, int W);

@@ -1,6 +1,7 @@
 // Structural-similarity and visual-information-fidelity families of reference core/metric.py
 // (calc_ssim :316-364, calc_msssim :368-402, calc_vif :406-458, calc_viff :461-491), the 16-metric
 // row of eval.py:29-75, and the C ABI entry points of the metric suite.
+#include <stdlib.h>
 #include "metrics.cuh"
 
 namespace mmif {
@@ -73,8 +74,14 @@ static int run_ssim_level(const float* a, const float* b, const float* f, int N,
     const double R = data_range;
     const long long npos = (long long)(H - k + 1) * (W - k + 1);
     dim3 grid((unsigned)((npos + 255) / 256), N);
-    ssim_small_kernel<<<grid, 256, 0, st>>>(a, b, f, H, W, k, taps, (0.01 * R) * (0.01 * R), (0.03 * R) * (0.03 * R), ws.partial,
-                                            ws.counters, sums, stride);
+    // The deep pyramid levels (image smaller than the window) keep counters + partials in the chain's own
+    // strip-kernel workspace: the chains of mmif_eval_suite run concurrently and the shared ws.partial
+    // belongs to the pixel kernel there.  A small window on a large image (mmif_ssim only) uses ws.partial.
+    const size_t small_need = ws_counters_bytes(N) + (size_t)N * grid.x * 8 * sizeof(double);
+    double* part = ws.partial; unsigned* cnt = ws.counters;
+    if (small_need <= ws.fwd_ws_bytes) { part = (double*)(ws.fwd_ws + ws_counters_bytes(N)); cnt = (unsigned*)ws.fwd_ws; }
+    ssim_small_kernel<<<grid, 256, 0, st>>>(a, b, f, H, W, k, taps, (0.01 * R) * (0.01 * R), (0.03 * R) * (0.03 * R), part, cnt,
+                                            sums, stride);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -318,13 +325,17 @@ size_t metric_ws_bytes(int N, int H, int W) {
     partial = partial > ps ? partial : ps;
     size_t fwd = 0;
     const LevelDims md = msssim_dims(H, W, 11);
-    for (int l = 0; l < 5; ++l) { const size_t b = fwd_ws_bytes(11, N, md.h[l], md.w[l]); fwd = fwd > b ? fwd : b; }
+    for (int l = 0; l < 5; ++l) {
+        size_t b = fwd_ws_bytes(11, N, md.h[l], md.w[l]);
+        if (md.k[l] < 11) b = ws_counters_bytes(N) + (size_t)N * (((size_t)md.h[l] * md.w[l] + 255) / 256) * 8 * sizeof(double);   // ssim_small_kernel
+        fwd = fwd > b ? fwd : b;
+    }
     const VifDims vd = vif_dims(H, W);
     for (int s = 0; s < 4; ++s) { const size_t b = fwd_ws_bytes(kVifWin[s], N, vd.h[s], vd.w[s]); fwd = fwd > b ? fwd : b; }
     const size_t pm = msssim_pyr_floats(N, H, W), pv = vif_pyr_floats(N, H, W);
     const size_t pyr = pm > pv ? pm : pv;
-    return al256((size_t)(N + 1) * 4) + al256(partial * 8) + al256(fwd) + al256(hist_extra_words(N) * 4) +
-           al256((size_t)N * kRawPerPair * 8) + al256(pyr * 4) + al256((size_t)N * MMIF_HIST_WORDS * 4) + 256;
+    return al256((size_t)(N + 1) * 4) + al256(partial * 8) + 2 * al256(fwd) + al256(hist_extra_words(N) * 4) +
+           al256((size_t)N * kRawPerPair * 8) + al256(pyr * 4) + al256(pv * 4) + al256((size_t)N * MMIF_HIST_WORDS * 4) + 256;
 }
 
 int carve_metric_ws(MetricWs* w, void* ws, size_t ws_bytes, int N, int H, int W) {
@@ -339,7 +350,11 @@ int carve_metric_ws(MetricWs* w, void* ws, size_t ws_bytes, int N, int H, int W)
     partial = partial > ps ? partial : ps;
     size_t fwd = 0;
     const LevelDims md = msssim_dims(H, W, 11);
-    for (int l = 0; l < 5; ++l) { const size_t b = fwd_ws_bytes(11, N, md.h[l], md.w[l]); fwd = fwd > b ? fwd : b; }
+    for (int l = 0; l < 5; ++l) {
+        size_t b = fwd_ws_bytes(11, N, md.h[l], md.w[l]);
+        if (md.k[l] < 11) b = ws_counters_bytes(N) + (size_t)N * (((size_t)md.h[l] * md.w[l] + 255) / 256) * 8 * sizeof(double);   // ssim_small_kernel
+        fwd = fwd > b ? fwd : b;
+    }
     const VifDims vd = vif_dims(H, W);
     for (int s = 0; s < 4; ++s) { const size_t b = fwd_ws_bytes(kVifWin[s], N, vd.h[s], vd.w[s]); fwd = fwd > b ? fwd : b; }
     const size_t pm = msssim_pyr_floats(N, H, W), pv = vif_pyr_floats(N, H, W);
@@ -349,7 +364,9 @@ int carve_metric_ws(MetricWs* w, void* ws, size_t ws_bytes, int N, int H, int W)
     w->hist_extra = (uint32_t*)p; p += al256(hist_extra_words(N) * 4);
     w->raw = (double*)p; p += al256((size_t)N * kRawPerPair * 8);
     w->pyr = (float*)p; w->pyr_floats = pm > pv ? pm : pv; p += al256(w->pyr_floats * 4);
-    w->counts = (uint32_t*)p;
+    w->counts = (uint32_t*)p; p += al256((size_t)N * MMIF_HIST_WORDS * 4);
+    w->fwd_ws_b = p; p += al256(fwd);
+    w->pyr_b = (float*)p;
     return MMIF_OK;
 }
 
@@ -487,6 +504,33 @@ extern "C" int mmif_viff(const float* a, const float* b, const float* f, int N, 
     return MMIF_OK;
 }
 
+// The four metric families of the suite are independent until the last (tiny) compose kernel: they are
+// forked onto three library-owned streams and joined back with events (no host synchronisation; legal
+// under stream capture), so the histogram kernel (one 1024-thread CTA per joint, i.e. 2N of the 148 SMs)
+// and the small pyramid levels overlap with the bandwidth- / FMA-bound kernels of the other families.
+struct SuiteFork { cudaStream_t s[3]; cudaEvent_t fork, join[3]; int dev; bool ok; };
+static SuiteFork* suite_fork() {
+    static thread_local SuiteFork tab[8];
+    static const bool serial = getenv("MMIF_SERIAL") != nullptr;
+    if (serial) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    SuiteFork* f = nullptr;
+    for (int i = 0; i < 8 && !f; ++i) {
+        if (tab[i].ok && tab[i].dev == dev) f = &tab[i];
+        else if (!tab[i].ok) {
+            SuiteFork& t = tab[i];
+            bool good = cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess;
+            for (int k = 0; k < 3 && good; ++k)
+                good = cudaStreamCreateWithFlags(&t.s[k], cudaStreamNonBlocking) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&t.join[k], cudaEventDisableTiming) == cudaSuccess;
+            if (!good) { (void)cudaGetLastError(); return nullptr; }
+            t.dev = dev; t.ok = true; f = &t;
+        }
+    }
+    return f;
+}
+
 extern "C" int mmif_eval_suite(const float* a, const float* b, const float* f, int N, int H, int W, double* out, void* ws,
                                size_t ws_bytes, void* stream) {
     int rc = check_imgs(a, b, f, N, H, W); if (rc) return rc;
@@ -494,12 +538,32 @@ extern "C" int mmif_eval_suite(const float* a, const float* b, const float* f, i
     if (H < 11 || W < 11) { set_error("eval suite needs H,W >= 11"); return MMIF_E_SHAPE; }
     MetricWs w; rc = carve_metric_ws(&w, ws, ws_bytes, N, H, W); if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_pixel_metrics(a, b, f, N, H, W, 1.5f, w.raw + RAW_STATS, kRawPerPair, w.raw + RAW_QABF, kRawPerPair, w, st); if (rc) return rc;
-    MMIF_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)N * MMIF_HIST_WORDS * 4, st));
-    rc = launch_hist(a, b, f, N, H, W, w.counts, w.raw + RAW_ENT, kRawPerPair, w, st); if (rc) return rc;
+    SuiteFork* fk = suite_fork();
+    cudaStream_t s_ms = st, s_px = st, s_hi = st;
+    if (fk) {
+        s_ms = fk->s[0]; s_px = fk->s[1]; s_hi = fk->s[2];
+        MMIF_CUDA(cudaEventRecord(fk->fork, st));
+        for (int k = 0; k < 3; ++k) MMIF_CUDA(cudaStreamWaitEvent(fk->s[k], fk->fork, 0));
+    }
+    MetricWs wv = w;                  // VIF chain (longest): caller's stream, its own strip workspace + pyramid
+    wv.fwd_ws = w.fwd_ws_b; wv.pyr = w.pyr_b;
+    int rc_v = run_vif(a, b, f, N, H, W, w.raw + RAW_VIF, kRawPerPair, wv, st);
     // level 0 of the MS-SSIM pyramid is calc_ssim(.., data_range=255) itself (metric.py:379-384)
-    rc = run_msssim(a, b, f, N, H, W, 11, 255.f, w.raw + RAW_MS, kRawPerPair, w, st); if (rc) return rc;
-    rc = run_vif(a, b, f, N, H, W, w.raw + RAW_VIF, kRawPerPair, w, st); if (rc) return rc;
+    int rc_m = run_msssim(a, b, f, N, H, W, 11, 255.f, w.raw + RAW_MS, kRawPerPair, w, s_ms);
+    int rc_p = launch_pixel_metrics(a, b, f, N, H, W, 1.5f, w.raw + RAW_STATS, kRawPerPair, w.raw + RAW_QABF, kRawPerPair, w, s_px);
+    int rc_h = MMIF_OK;
+    if (cudaMemsetAsync(w.counts, 0, (size_t)N * MMIF_HIST_WORDS * 4, s_hi) != cudaSuccess) rc_h = cuda_fail(cudaGetLastError(), "memset");
+    if (!rc_h) rc_h = launch_hist(a, b, f, N, H, W, w.counts, w.raw + RAW_ENT, kRawPerPair, w, s_hi);
+    if (fk) {                          // always join, even after a launch error, so the streams stay ordered
+        for (int k = 0; k < 3; ++k) {
+            MMIF_CUDA(cudaEventRecord(fk->join[k], fk->s[k]));
+            MMIF_CUDA(cudaStreamWaitEvent(st, fk->join[k], 0));
+        }
+    }
+    if (rc_v) return rc_v;
+    if (rc_m) return rc_m;
+    if (rc_p) return rc_p;
+    if (rc_h) return rc_h;
     suite_out_kernel<<<ceil_div(N, 128), 128, 0, st>>>(w.raw, N, msssim_dims(H, W, 11), 1.0 / ((double)(H - 10) * (W - 10)), out);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
