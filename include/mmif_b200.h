@@ -140,6 +140,13 @@ int mmif_tv_loss(const float* x, int N, int H, int W, int norm, float weight, do
 int mmif_tv_loss_bwd(const float* x, int N, int H, int W, int norm, float weight, const float* gout1, float* gx,
                      void* stream);
 
+/* size_average=False of calc_ssim (reference loss.py:52-110 / metric.py:316-364): SSIM, CS and clamp(sigma1^2, 1e-4)
+ * MAPS of the pairs (i1, f), (i2, f), each [B][H-10][W-10]; any of the six outputs may be NULL.  11-tap window.
+ * ws from mmif_loss_workspace_bytes. */
+int mmif_ssim_maps(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
+                   float* ssim1, float* cs1, float* sigma1, float* ssim2, float* cs2, float* sigma2,
+                   void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- metric suite ----------- */
 /* All metric entries are batched over N independent pairs (a[n], b[n], f[n]) of one shape and
  * write doubles per pair.  ws from mmif_metric_workspace_bytes. */
@@ -213,6 +220,24 @@ int mmif_eval_suite(const float* a, const float* b, const float* f, int N, int H
 int mmif_eval_suite_host(const float* a_host, const float* b_host, const float* f_host, int N, int H,
                          int W, double* out_host, float* dev_scratch, double* dev_out,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---- uint8 ingest: eval.py:182-194 decodes 8-bit images with cv2 and widens them to float32 on the
+ * host; these entries take the 8-bit pixels and widen on the device (4x less host->device traffic, identical results:
+ * the widening is exact).  dev_scratch: 3*N*H*W floats (device).  The _host form copies from host memory into
+ * dev_u8 (3 * roundup16(N*H*W) bytes, device), runs the suite, copies the rows back and synchronises `stream`. */
+int mmif_widen_u8(const unsigned char* src, size_t n, float* dst, void* stream);
+int mmif_eval_suite_u8(const unsigned char* a, const unsigned char* b, const unsigned char* f, int N, int H, int W,
+                       double* out, float* dev_scratch, void* ws, size_t ws_bytes, void* stream);
+int mmif_eval_suite_u8_host(const unsigned char* a_host, const unsigned char* b_host, const unsigned char* f_host,
+                            int N, int H, int W, double* out_host, unsigned char* dev_u8, float* dev_scratch,
+                            double* dev_out, void* ws, size_t ws_bytes, void* stream);
+
+/* NormLoss (reference loss.py:361-385): out[0] = weight * mean(|x|) (MMIF_NORM_L1) or weight * mean(x^2) over the n
+ * elements of x (device double); ws: mmif_norm_workspace_bytes() bytes, zero-initialised once, 8-byte aligned.
+ * _bwd: gx[i] = gout1[0] * weight / n * sign(x[i]) (or 2 x[i]). */
+size_t mmif_norm_workspace_bytes(void);
+int mmif_norm_loss(const float* x, size_t n, int norm, float weight, double* out, void* ws, size_t ws_bytes, void* stream);
+int mmif_norm_loss_bwd(const float* x, size_t n, int norm, float weight, const float* gout1, float* gx, void* stream);
 
 #ifdef __cplusplus
 }

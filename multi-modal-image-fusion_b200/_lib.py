@@ -15,7 +15,8 @@ SYMBOLS = [
     'mmif_loss_workspace_bytes', 'mmif_loss_out_doubles', 'mmif_fusion_loss_fwd', 'mmif_fusion_loss_bwd',
     'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
     'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_ssim',
-    'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host',
+    'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8',
+    'mmif_eval_suite_u8', 'mmif_eval_suite_u8_host', 'mmif_norm_workspace_bytes', 'mmif_norm_loss', 'mmif_norm_loss_bwd',
 ]
 
 COMBINE = {'max': 0, 'avg': 1}
@@ -78,6 +79,14 @@ def load():
     lib.mmif_viff.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]
     lib.mmif_eval_suite.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]
     lib.mmif_eval_suite_host.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, sz, vp]
+    lib.mmif_ssim_maps.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.mmif_widen_u8.argtypes = [vp, sz, vp, vp]
+    lib.mmif_eval_suite_u8.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, sz, vp]
+    lib.mmif_eval_suite_u8_host.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, sz, vp]
+    lib.mmif_norm_workspace_bytes.restype = sz
+    lib.mmif_norm_workspace_bytes.argtypes = []
+    lib.mmif_norm_loss.argtypes = [vp, sz, ci, cf, vp, vp, sz, vp]
+    lib.mmif_norm_loss_bwd.argtypes = [vp, sz, ci, cf, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)  # every declared symbol must be exported
     _lib = lib

@@ -9,8 +9,9 @@ version), and a single autograd node with three outputs receives all three upstr
 
 Built on the same kernels: 'w-ssim' (per-sample gamma weights in the backward kernel), 'ms-ssim'
 (one SSIM forward/backward launch per pyramid level + pooling adjoints), use_padding=True (reflect-pad
-operator + its adjoint), TVLoss forward/backward.  Not built yet (raise NotImplementedError, never a
-silent fallback): size_average=False (SSIM maps), MSW_SSIM with use_padding, gradients w.r.t. the sources.
+operator + its adjoint, applied per pyramid level / per window for 'ms-ssim' / 'msw-ssim'), size_average=False
+(SSIM / CS / sigma maps), data_range=None auto-detect, TVLoss and NormLoss forward/backward.  Not built (raise
+NotImplementedError, never a silent fallback): gradients w.r.t. the sources, gradients through SSIM.forward's dict.
 'msw-ssim' runs the same forward / backward kernels with the 11/9/7/5/3 windows and per-position weights.
 """
 import ctypes
@@ -199,6 +200,29 @@ class _WeightedSSIM(torch.autograd.Function):
         return None, None, dF.view(ctx.in_shape), None
 
 
+def _pad_raw(x, pad):
+    """(B,H,W) -> reflect-padded (B,H+2p,W+2p); F.pad(.., 'reflect') of use_padding=True (loss.py:45-47)."""
+    lib = L.load()
+    B, H, W = x.shape
+    if pad >= H or pad >= W:
+        raise L.MmifError(f'reflect padding {pad} needs H, W > {pad}, got {(H, W)} (torch raises here too)')
+    out = torch.empty(B, H + 2 * pad, W + 2 * pad, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(lib.mmif_reflect_pad(x.data_ptr(), B, H, W, pad, out.data_ptr(), L.stream_ptr(x.device)))
+    return out
+
+
+def _pad_bwd_raw(g, pad):
+    """Adjoint of _pad_raw: (B,H+2p,W+2p) gradient folded back onto (B,H,W)."""
+    lib = L.load()
+    B, Hp, Wp = g.shape
+    H, W = Hp - 2 * pad, Wp - 2 * pad
+    out = torch.empty(B, H, W, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        L.check(lib.mmif_reflect_pad_bwd(g.data_ptr(), B, H, W, pad, out.data_ptr(), L.stream_ptr(g.device)))
+    return out
+
+
 def _halve(x):
     lib = L.load()
     B, H, W = x.shape
@@ -210,27 +234,32 @@ def _halve(x):
 
 class _MSSSIM(torch.autograd.Function):
     """calc_msssim of the loss module (loss.py:113-160) for the pairs (img1, imgf), (img2, imgf):
-    returns the two per-sample MS-SSIM vectors.  Backward: one SSIM-backward launch per level (cs on
-    levels 0..3, ssim on level 4, per-sample chain-rule factors) + the pooling adjoints."""
+    returns the two per-sample MS-SSIM vectors.  use_padding reflect-pads EVERY level by 5 before its
+    blur (calc_ssim -> _gaussian_fn, loss.py:45-47) while the pyramid pools the unpadded level
+    (loss.py:147-153).  Backward: one SSIM-backward launch per level (cs on levels 0..3, ssim on level
+    4, per-sample chain-rule factors) + the padding and pooling adjoints."""
 
     @staticmethod
-    def forward(ctx, img1, img2, imgf, data_range):
+    def forward(ctx, img1, img2, imgf, data_range, use_padding=False):
         x1, x2, y = _prep3(img1, img2, imgf)
         wts = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float32, device=y.device)
-        levels, vals = [], []
+        levels, vals, ranges = [], [], []
         for lvl in range(5):
-            if min(y.shape[-2:]) < 11:
-                raise L.MmifError(f'ms-ssim: level {lvl} is {tuple(y.shape[-2:])}, smaller than the 11-tap window '
+            if min(y.shape[-2:]) < (6 if use_padding else 11):
+                raise L.MmifError(f'ms-ssim: level {lvl} is {tuple(y.shape[-2:])}, too small for the 11-tap window '
                                   '(the reference fails here too)')
-            ps = _fwd_per_sample(x1, x2, y, data_range)
+            lx1, lx2, ly = (_pad_raw(x1, 5), _pad_raw(x2, 5), _pad_raw(y, 5)) if use_padding else (x1, x2, y)
+            dr = _auto_range(x1) if data_range is None else data_range     # per level, from the level's img1 (loss.py:60-65)
+            ranges.append(dr)
+            ps = _fwd_per_sample(lx1, lx2, ly, dr)
             vals.append(torch.stack([ps[:, 1], ps[:, 4]], dim=1) if lvl < 4 else torch.stack([ps[:, 0], ps[:, 3]], dim=1))
-            levels.append((x1, x2, y))
+            levels.append((lx1, lx2, ly))
             if lvl < 4:
                 x1, x2, y = _halve(x1), _halve(x2), _halve(y)
         v = torch.stack(vals, dim=0).to(torch.float32)              # (5, B, 2)
         vc = v.clamp(min=eps)
         ms = torch.prod(vc ** wts.view(5, 1, 1), dim=0)              # (B, 2)
-        ctx.levels, ctx.data_range, ctx.in_shape = levels, data_range, imgf.shape
+        ctx.levels, ctx.ranges, ctx.in_shape, ctx.use_padding = levels, ranges, imgf.shape, use_padding
         ctx.save_for_backward(v, vc, ms, wts)
         return ms[:, 0].contiguous(), ms[:, 1].contiguous()
 
@@ -245,37 +274,42 @@ class _MSSSIM(torch.autograd.Function):
         fac = g.unsqueeze(0) * wts.view(5, 1, 1) * ms.unsqueeze(0) / vc * (v >= eps).to(torch.float32)   # (5, B, 2)
         grads = []
         for lvl, (x1, x2, y) in enumerate(ctx.levels):
-            grads.append(_ssim_bwd_ex(x1, x2, y, ctx.data_range, one, fac[lvl], 1 if lvl < 4 else 0, 1.0))
+            gl = _ssim_bwd_ex(x1, x2, y, ctx.ranges[lvl], one, fac[lvl], 1 if lvl < 4 else 0, 1.0)
+            grads.append(_pad_bwd_raw(gl, 5) if ctx.use_padding else gl)
         for lvl in range(4, 0, -1):
             Bn, H, W = grads[lvl - 1].shape
             with torch.cuda.device(ms.device):
                 L.check(lib.mmif_halve_bwd(grads[lvl].data_ptr(), Bn, H, W, grads[lvl - 1].data_ptr(), L.stream_ptr(ms.device)))
-        return None, None, grads[0].view(ctx.in_shape), None
+        return None, None, grads[0].view(ctx.in_shape), None, None
 
 
 class _MSWSSIM(torch.autograd.Function):
     """MSW_SSIM.forward (loss.py:226-237): windows 11/9/7/5/3 (sigma by loss.py:34), per-position
-    gamma = sigma1/(sigma1+sigma2) from the SOURCE variances (a constant of the backward)."""
+    gamma = sigma1/(sigma1+sigma2) from the SOURCE variances (a constant of the backward).
+    use_padding reflect-pads by win//2 per window (loss.py:45-47), so every window sees H x W positions."""
 
     @staticmethod
-    def forward(ctx, img1, img2, imgf, data_range, win_sizes):
+    def forward(ctx, img1, img2, imgf, data_range, win_sizes, use_padding=False):
         lib = L.load()
         x1, x2, y = _prep3(img1, img2, imgf)
         B, H, W = y.shape
         dev = y.device
-        nws = lib.mmif_loss_workspace_bytes(B, H, W)
-        if nws == 0:
-            raise L.MmifError(f'unsupported shape {(B, H, W)}')
-        ws = L.workspace(dev, nws, 'loss', (B, H, W))
         total = torch.zeros((), dtype=torch.float64, device=dev)
         for k in win_sizes:
+            p = k // 2 if use_padding else 0
+            a1, a2, ay = (_pad_raw(x1, p), _pad_raw(x2, p), _pad_raw(y, p)) if p else (x1, x2, y)
+            Hp, Wp = ay.shape[-2:]
+            nws = lib.mmif_loss_workspace_bytes(B, Hp, Wp)
+            if nws == 0:
+                raise L.MmifError(f'unsupported shape {(B, Hp, Wp)}')
+            ws = L.workspace(dev, nws, 'loss', (B, Hp, Wp))
             sums = torch.empty(B * 8, dtype=torch.float64, device=dev)
             with torch.cuda.device(dev):
-                L.check(lib.mmif_mswssim_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(k), float(data_range),
+                L.check(lib.mmif_mswssim_fwd(a1.data_ptr(), a2.data_ptr(), ay.data_ptr(), B, Hp, Wp, int(k), float(data_range),
                                              sums.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
-            total = total + sums.view(B, 8)[:, 0].sum() / (B * (H - k + 1) * (W - k + 1))
+            total = total + sums.view(B, 8)[:, 0].sum() / (B * (Hp - k + 1) * (Wp - k + 1))
         ctx.save_for_backward(x1, x2, y)
-        ctx.data_range, ctx.win_sizes, ctx.in_shape = data_range, tuple(win_sizes), imgf.shape
+        ctx.data_range, ctx.win_sizes, ctx.in_shape, ctx.use_padding = data_range, tuple(win_sizes), imgf.shape, use_padding
         return (total / len(win_sizes)).to(torch.float32)
 
     @staticmethod
@@ -286,14 +320,21 @@ class _MSWSSIM(torch.autograd.Function):
         dev = y.device
         dF = torch.empty_like(y)
         g1 = g.to(torch.float32).reshape(1).contiguous()
-        ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
         scale = 1.0 / (B * len(ctx.win_sizes))
         for i, k in enumerate(ctx.win_sizes):
+            p = k // 2 if ctx.use_padding else 0
+            a1, a2, ay = (_pad_raw(x1, p), _pad_raw(x2, p), _pad_raw(y, p)) if p else (x1, x2, y)
+            Hp, Wp = ay.shape[-2:]
+            ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, Hp, Wp), 'loss', (B, Hp, Wp))
+            dst = torch.empty_like(ay) if p else dF
             with torch.cuda.device(dev):
-                L.check(lib.mmif_mswssim_bwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(k), float(ctx.data_range),
-                                             g1.data_ptr(), scale, 1 if i else 0, dF.data_ptr(), ws.data_ptr(), ws.numel(),
-                                             L.stream_ptr(dev)))
-        return None, None, dF.view(ctx.in_shape), None, None
+                L.check(lib.mmif_mswssim_bwd(a1.data_ptr(), a2.data_ptr(), ay.data_ptr(), B, Hp, Wp, int(k), float(ctx.data_range),
+                                             g1.data_ptr(), scale, 1 if (i and not p) else 0, dst.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), L.stream_ptr(dev)))
+            if p:
+                folded = _pad_bwd_raw(dst, p)
+                dF = folded if i == 0 else dF.add_(folded)
+        return None, None, dF.view(ctx.in_shape), None, None, None
 
 
 class _ReflectPad(torch.autograd.Function):
@@ -380,16 +421,39 @@ def _ssim_dict(img1, img2, data_range, use_padding, size_average, win_size=11):
             raise NotImplementedError('only the 11-tap window of the training objective is built')
         img1, img2 = _ReflectPad.apply(img1, 5), _ReflectPad.apply(img2, 5)
         use_padding = False
-    if not size_average:
-        raise NotImplementedError('size_average=False (per-pixel SSIM maps) is not built yet')
     if win_size != 11:
         raise NotImplementedError('only the 11-tap window of the training objective is built')
     if data_range is None:
         data_range = _auto_range(img1)
     if img2.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError('SSIM.forward is forward-only here; use SSIMLoss for the differentiable objective')
+    if not size_average:
+        return ssim_maps(img1, img2, data_range)
     _, _, _, ps = _fused(img1, img1, img2, data_range=data_range)
     return {'ssim': ps[:, 0], 'cs': ps[:, 1], 'sigma': ps[:, 2]}
+
+
+def ssim_maps(img1, img2, data_range):
+    """size_average=False of calc_ssim (loss.py:99-108): the dict of (B,1,H-10,W-10) maps."""
+    lib = L.load()
+    for t, nm in ((img1, 'img1'), (img2, 'img2')):
+        L.require_cuda(t, nm)
+    x, B, H, W = L.as_f32_3d(img1.detach(), 'img1')
+    y, _, _, _ = L.as_f32_3d(img2.detach(), 'img2')
+    if y.shape != x.shape:
+        raise L.MmifError(f'shape mismatch: {tuple(img1.shape)} {tuple(img2.shape)}')
+    dev = x.device
+    L.ensure_device(dev)
+    nws = lib.mmif_loss_workspace_bytes(B, H, W)
+    if nws == 0:
+        raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11')
+    ws = L.workspace(dev, nws, 'loss', (B, H, W))
+    maps = [torch.empty(B, 1, H - 10, W - 10, dtype=torch.float32, device=dev) for _ in range(3)]
+    with torch.cuda.device(dev):
+        L.check(lib.mmif_ssim_maps(x.data_ptr(), x.data_ptr(), y.data_ptr(), B, H, W, float(data_range), maps[0].data_ptr(),
+                                   maps[1].data_ptr(), maps[2].data_ptr(), None, None, None, ws.data_ptr(), ws.numel(),
+                                   L.stream_ptr(dev)))
+    return {'ssim': maps[0], 'cs': maps[1], 'sigma': maps[2]}
 
 
 class SSIM(nn.Module):
@@ -420,10 +484,7 @@ class MS_SSIM(SSIM):
             raise NotImplementedError('only the 11-tap window of the training objective is built')
         if not self.size_average:
             raise NotImplementedError('size_average=False is not built yet')
-        if self.use_padding:
-            img1, img2 = _ReflectPad.apply(img1, 5), _ReflectPad.apply(img2, 5)
-        dr = _auto_range(img1) if self.data_range is None else self.data_range
-        return _MSSSIM.apply(img1, img1, img2, dr)[0]
+        return _MSSSIM.apply(img1, img1, img2, self.data_range, bool(self.use_padding))[0]
 
 
 class MSW_SSIM(nn.Module):
@@ -439,10 +500,8 @@ class MSW_SSIM(nn.Module):
     def forward(self, img1, img2, imgf):
         if any(k not in (11, 9, 7, 5, 3) for k in self.win_sizes):
             raise NotImplementedError('MSW_SSIM: windows 11, 9, 7, 5, 3 are built')
-        if self.use_padding:
-            raise NotImplementedError('MSW_SSIM with use_padding=True is not built yet')
         dr = _auto_range(img1) if self.data_range is None else self.data_range
-        return _MSWSSIM.apply(img1, img2, imgf, dr, tuple(self.win_sizes))
+        return _MSWSSIM.apply(img1, img2, imgf, dr, tuple(self.win_sizes), bool(self.use_padding))
 
 
 class SSIMLoss(nn.Module):
@@ -456,19 +515,20 @@ class SSIMLoss(nn.Module):
         self.weight = weight
 
     def forward(self, img1, img2, imgf):
-        if self.mode in ('ssim', 'w-ssim', 'ms-ssim') and self.use_padding:
+        if self.mode in ('ssim', 'w-ssim') and self.use_padding:
             img1, img2, imgf = _pad3(img1, img2, imgf)      # reflect pad 5, then the valid-window path (loss.py:45-47)
+        dr = _auto_range(img1) if self.data_range is None else self.data_range     # loss.py:60-65
         if self.mode == 'ssim':
-            loss, _, _, _ = _fused(img1, img2, imgf, data_range=self.data_range, w_ssim=self.weight)
+            loss, _, _, _ = _fused(img1, img2, imgf, data_range=dr, w_ssim=self.weight)
             return loss
         elif self.mode == 'w-ssim':
-            loss = _WeightedSSIM.apply(img1, img2, imgf, self.data_range)
+            loss = _WeightedSSIM.apply(img1, img2, imgf, dr)
             return self.weight * (1.0 - loss)
         elif self.mode == 'ms-ssim':
-            m1, m2 = _MSSSIM.apply(img1, img2, imgf, self.data_range)
+            m1, m2 = _MSSSIM.apply(img1, img2, imgf, self.data_range, bool(self.use_padding))
             return self.weight * (1.0 - (m1.mean() + m2.mean()) * 0.5)
         elif self.mode == 'msw-ssim':
-            loss = MSW_SSIM((11, 9, 7, 5, 3), self.data_range, self.use_padding)(img1, img2, imgf)
+            loss = MSW_SSIM((11, 9, 7, 5, 3), dr, self.use_padding)(img1, img2, imgf)
             return self.weight * (1.0 - loss)
         else:
             raise ValueError("only supported ['ssim', 'w-ssim', 'ms-ssim', 'msw-ssim'] mode")
@@ -524,9 +584,41 @@ class TVLoss(nn.Module):
         return _TV.apply(x, self.mode, self.weight)
 
 
+class _Norm(torch.autograd.Function):
+    """NormLoss (loss.py:361-385) forward + backward on the device kernels."""
+
+    @staticmethod
+    def forward(ctx, x, mode, weight):
+        lib = L.load()
+        L.require_cuda(x, 'x')
+        if x.dtype != torch.float32:
+            raise L.MmifError(f'NormLoss: float32 expected, got {x.dtype}')
+        xc = x.detach().contiguous()
+        dev = xc.device
+        L.ensure_device(dev)
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+        ws = L.workspace(dev, lib.mmif_norm_workspace_bytes(), 'norm')
+        with torch.cuda.device(dev):
+            L.check(lib.mmif_norm_loss(xc.data_ptr(), xc.numel(), L.NORM[mode], float(weight), out.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), L.stream_ptr(dev)))
+        ctx.save_for_backward(xc)
+        ctx.mode, ctx.weight, ctx.in_shape = mode, weight, x.shape
+        return out[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        xc, = ctx.saved_tensors
+        gx = torch.empty_like(xc)
+        g1 = g.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(xc.device):
+            L.check(lib.mmif_norm_loss_bwd(xc.data_ptr(), xc.numel(), L.NORM[ctx.mode], float(ctx.weight), g1.data_ptr(),
+                                           gx.data_ptr(), L.stream_ptr(xc.device)))
+        return gx.view(ctx.in_shape), None, None
+
+
 class NormLoss(nn.Module):
-    '''reference loss.py:361-385.  A plain reduction of an arbitrary tensor: kept in torch (it is
-    not on the fused path; PixelLoss/GradLoss compute their norms inside the fused kernel).'''
+    '''reference loss.py:361-385: weight * mean(|x|) ('l1') or weight * mean(x^2) ('l2') of any tensor.'''
 
     def __init__(self, mode='l1', weight=1.0):
         super(NormLoss, self).__init__()
@@ -535,6 +627,4 @@ class NormLoss(nn.Module):
 
     def forward(self, x):
         _check_norm(self.mode)
-        L.require_cuda(x, 'x')
-        v = torch.abs(x).mean() if self.mode == 'l1' else torch.pow(x, 2).mean()
-        return self.weight * v
+        return _Norm.apply(x, self.mode, self.weight)

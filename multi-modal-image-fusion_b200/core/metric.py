@@ -147,22 +147,69 @@ def _qabf(a, b, f, Lexp):
     return _memo.get('qabf', (a, b, f), float(Lexp), run)
 
 
-def _ssim2(a, b, f, win_size, data_range, use_padding):
+def _pad_dev(t, pad):
+    """reflect-pad (N,H,W) device images by `pad` (use_padding=True, metric.py:305-311)."""
+    lib = L.load()
+    n, h, w = t.shape
+    if pad >= h or pad >= w:
+        raise L.MmifError(f'reflect padding {pad} needs H, W > {pad}, got {(h, w)} (torch raises here too)')
+    out = torch.empty(n, h + 2 * pad, w + 2 * pad, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        L.check(lib.mmif_reflect_pad(t.data_ptr(), n, h, w, pad, out.data_ptr(), L.stream_ptr(t.device)))
+    return out
+
+
+def _halve_dev(t):
+    lib = L.load()
+    n, h, w = t.shape
+    out = torch.empty(n, (h + 1) // 2, (w + 1) // 2, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        L.check(lib.mmif_halve(t.data_ptr(), n, h, w, out.data_ptr(), L.stream_ptr(t.device)))
+    return out
+
+
+def _ssim_level(imgs, shape, win_size, data_range, use_padding):
+    """(n,4) [ssim_af, cs_af, ssim_bf, cs_bf] of one level; use_padding pads by min(win,h,w)//2 first."""
+    n, h, w = shape
     if use_padding:
-        raise NotImplementedError('use_padding=True is not built yet')
+        p = min(int(win_size), h, w) // 2
+        if p:
+            imgs = [_pad_dev(t.view(n, h, w), p) for t in imgs]
+            shape = (n, h + 2 * p, w + 2 * p)
+    return _call('mmif_ssim', imgs, shape, 4, int(win_size) if not use_padding else min(int(win_size), h, w),
+                 ctypes.c_float(data_range), 0)
+
+
+def _ssim2(a, b, f, win_size, data_range, use_padding):
     def run():
         imgs, shape, _ = _prep(a, b, f)
-        return _call('mmif_ssim', imgs, shape, 4, int(win_size), ctypes.c_float(data_range), 0)
-    return _memo.get('ssim', (a, b, f), (int(win_size), float(data_range)), run)
+        return _ssim_level(imgs, shape, win_size, data_range, use_padding)
+    return _memo.get('ssim', (a, b, f), (int(win_size), float(data_range), bool(use_padding)), run)
 
 
 def _msssim2(a, b, f, win_size, data_range, use_padding):
-    if use_padding:
-        raise NotImplementedError('use_padding=True is not built yet')
     def run():
         imgs, shape, _ = _prep(a, b, f)
-        return _call('mmif_msssim', imgs, shape, L.MSSSIM_DOUBLES, int(win_size), ctypes.c_float(data_range))
-    return _memo.get('msssim', (a, b, f), (int(win_size), float(data_range)), run)
+        if not use_padding:
+            return _call('mmif_msssim', imgs, shape, L.MSSSIM_DOUBLES, int(win_size), ctypes.c_float(data_range))
+        # use_padding=True pads every level before its blur while the pyramid pools the unpadded level
+        # (metric.py:378-400): composed level by level from the same device kernels
+        n, h, w = shape
+        wts = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float64, device=imgs[0].device)
+        cur = [t.view(n, h, w) for t in imgs]
+        vals = []
+        for lvl in range(5):
+            hh, ww = cur[0].shape[-2:]
+            r = _ssim_level(cur, (n, hh, ww), win_size, data_range, True)     # window = min(win, h, w) per level (metric.py:323-325)
+            vals.append(torch.stack([r[:, 1], r[:, 3]], dim=1) if lvl < 4 else torch.stack([r[:, 0], r[:, 2]], dim=1))
+            if lvl < 4:
+                cur = [_halve_dev(t) for t in cur]
+        v = torch.stack(vals, dim=0).clamp(min=1e-7)       # (5, n, 2)
+        ms = torch.prod(v ** wts.view(5, 1, 1), dim=0)
+        out = torch.zeros(n, L.MSSSIM_DOUBLES, dtype=torch.float64, device=ms.device)
+        out[:, 0], out[:, 1] = ms[:, 0], ms[:, 1]
+        return out
+    return _memo.get('msssim', (a, b, f), (int(win_size), float(data_range), bool(use_padding)), run)
 
 
 def _viff3(a, b, f):
@@ -278,11 +325,32 @@ def calc_Labf(img1, img2, imgf, L=1.5):
 def calc_ssim(img1, img2, win_size=11, data_range=255.0, use_padding=False, size_average=True, full=False):
     _single(img1, 'calc_ssim')
     if not size_average:
-        raise NotImplementedError('size_average=False (SSIM maps) is not built yet')
+        return _ssim_map(img1, img2, win_size, data_range, use_padding, full)
     r = _ssim2(img1, img1, img2, win_size, data_range, use_padding)
     if full:
         return _scalar(r[0, 0], img1.device), _scalar(r[0, 1], img1.device)
     return _scalar(r[0, 0], img1.device)
+
+
+def _ssim_map(img1, img2, win_size, data_range, use_padding, full):
+    """size_average=False (metric.py:357-364): the (1,1,H',W') SSIM map (and CS map with full=True)."""
+    lib = L.load()
+    imgs, (n, h, w), home = _prep(img1, img2)
+    if min(int(win_size), h, w) != 11:
+        raise NotImplementedError('SSIM maps are built for the 11-tap window (images of at least 11 x 11)')
+    if use_padding:
+        imgs = [_pad_dev(t.view(n, h, w), 5) for t in imgs]
+        h, w = h + 10, w + 10
+    dev = imgs[0].device
+    nws = lib.mmif_loss_workspace_bytes(n, h, w)
+    ws = L.workspace(dev, nws, 'loss', (n, h, w))
+    maps = [torch.empty(n, 1, h - 10, w - 10, dtype=torch.float32, device=dev) for _ in range(2)]
+    with torch.cuda.device(dev):
+        L.check(lib.mmif_ssim_maps(imgs[0].data_ptr(), imgs[0].data_ptr(), imgs[1].data_ptr(), n, h, w, float(data_range),
+                                   maps[0].data_ptr(), maps[1].data_ptr(), None, None, None, None, ws.data_ptr(), ws.numel(),
+                                   L.stream_ptr(dev)))
+    maps = [m.to(home) if m.device != home else m for m in maps]
+    return (maps[0], maps[1]) if full else maps[0]
 
 
 # 17. msssim
@@ -304,6 +372,37 @@ def eval_metrics_batch(img1, img2, imgf):
         L.require_cuda(t, 'image')
     imgs, shape, _ = _prep(img1, img2, imgf)
     return _call('mmif_eval_suite', imgs, shape, L.EVAL_METRICS)
+
+
+def eval_metrics_batch_u8(img1, img2, imgf):
+    """uint8 ingest: (N,1,H,W) / (N,H,W) uint8 tensors — CUDA, or pinned / pageable HOST tensors (one H2D copy of
+    1 byte per pixel per image) -> (N,16) float64 rows on the GPU.  Same results as widening on the host
+    (eval.py:182-194) followed by eval_metrics_batch: the device widening is exact."""
+    lib = L.load()
+    ts = []
+    for t in (img1, img2, imgf):
+        if t.dtype != torch.uint8:
+            raise L.MmifError(f'uint8 expected, got {t.dtype}')
+        if t.dim() == 4:
+            if t.shape[1] != 1:
+                raise L.MmifError(f'single-channel (N,1,H,W) expected, got {tuple(t.shape)}')
+            t = t[:, 0]
+        elif t.dim() == 2:
+            t = t.unsqueeze(0)
+        ts.append(t.contiguous())
+    n, h, w = ts[0].shape
+    if any(tuple(t.shape) != (n, h, w) for t in ts):
+        raise L.MmifError('shape mismatch between the three images')
+    dev = ts[0].device if ts[0].is_cuda else _default_device()
+    L.ensure_device(dev)
+    ts = [t.to(dev, non_blocking=True) for t in ts]
+    scratch = torch.empty(3 * n * h * w, dtype=torch.float32, device=dev)
+    out = torch.empty(n * L.EVAL_METRICS, dtype=torch.float64, device=dev)
+    ws = _ws(dev, n, h, w)
+    with torch.cuda.device(dev):
+        L.check(lib.mmif_eval_suite_u8(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), n, h, w, out.data_ptr(),
+                                       scratch.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+    return out.view(n, L.EVAL_METRICS)
 
 
 def eval_metrics(img1, img2, imgf):

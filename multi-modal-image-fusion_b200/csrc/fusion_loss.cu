@@ -600,6 +600,24 @@ extern "C" int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f
     return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
 }
 
+/* size_average=False of calc_ssim (loss.py:52-110, metric.py:316-364): the SSIM / CS / clamped-variance MAPS of the
+ * pairs (i1, f) and (i2, f), each [B][H-10][W-10] (any of the six may be NULL).  11-tap window, sigma 1.5. */
+extern "C" int mmif_ssim_maps(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
+                              float* ssim1, float* cs1, float* sigma1, float* ssim2, float* cs2, float* sigma2, void* ws,
+                              size_t ws_bytes, void* stream) {
+    int rc = check_common(i1, i2, f, B, H, W);
+    if (rc) return rc;
+    const size_t core = loss_ws_core_bytes(B, H, W);
+    if (!ws || ws_bytes < core + (size_t)B * 8 * sizeof(double)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
+    FwdLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.win = WIN11; L.sigma = 1.5; L.epi = EPI_MAPS; L.finalize = FIN_SUMS; L.data_range = data_range;
+    L.cfg.pixel_norm = L.cfg.grad_norm = MMIF_NORM_L1;
+    L.maps[0] = ssim1; L.maps[1] = cs1; L.maps[2] = sigma1; L.maps[3] = ssim2; L.maps[4] = cs2; L.maps[5] = sigma2;
+    double* sums = (double*)((unsigned char*)ws + core);
+    return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, nullptr, ws, core, (cudaStream_t)stream);
+}
+
 static double loss_sigma_of(int win) { return win == 11 ? 1.5 : 0.15 * (win - 1); }     // loss.py:34
 static bool msw_win_ok(int win) { return win == 11 || win == 9 || win == 7 || win == 5 || win == 3; }
 

@@ -586,6 +586,37 @@ extern "C" int mmif_eval_suite_host(const float* a_host, const float* b_host, co
     return MMIF_OK;
 }
 
+extern "C" int mmif_widen_u8(const unsigned char* src, size_t n, float* dst, void* stream);
+
+extern "C" int mmif_eval_suite_u8(const unsigned char* a, const unsigned char* b, const unsigned char* f, int N, int H, int W,
+                                  double* out, float* dev_scratch, void* ws, size_t ws_bytes, void* stream) {
+    if (!a || !b || !f || !dev_scratch) { set_error("null pointer"); return MMIF_E_NULL; }
+    if (N < 1 || H < 1 || W < 1) { set_error("bad shape"); return MMIF_E_SHAPE; }
+    const size_t n = (size_t)N * H * W;
+    int rc = mmif_widen_u8(a, n, dev_scratch, stream); if (rc) return rc;
+    rc = mmif_widen_u8(b, n, dev_scratch + n, stream); if (rc) return rc;
+    rc = mmif_widen_u8(f, n, dev_scratch + 2 * n, stream); if (rc) return rc;
+    return mmif_eval_suite(dev_scratch, dev_scratch + n, dev_scratch + 2 * n, N, H, W, out, ws, ws_bytes, stream);
+}
+
+extern "C" int mmif_eval_suite_u8_host(const unsigned char* a_host, const unsigned char* b_host, const unsigned char* f_host, int N,
+                                       int H, int W, double* out_host, unsigned char* dev_u8, float* dev_scratch, double* dev_out,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    if (!a_host || !b_host || !f_host || !out_host || !dev_u8 || !dev_scratch || !dev_out) { set_error("null pointer"); return MMIF_E_NULL; }
+    if (N < 1 || H < 1 || W < 1) { set_error("bad shape"); return MMIF_E_SHAPE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)N * H * W;
+    const size_t n16 = (n + 15) / 16 * 16;                       // keep the three device images 16-byte aligned
+    MMIF_CUDA(cudaMemcpyAsync(dev_u8, a_host, n, cudaMemcpyHostToDevice, st));
+    MMIF_CUDA(cudaMemcpyAsync(dev_u8 + n16, b_host, n, cudaMemcpyHostToDevice, st));
+    MMIF_CUDA(cudaMemcpyAsync(dev_u8 + 2 * n16, f_host, n, cudaMemcpyHostToDevice, st));
+    int rc = mmif_eval_suite_u8(dev_u8, dev_u8 + n16, dev_u8 + 2 * n16, N, H, W, dev_out, dev_scratch, ws, ws_bytes, stream);
+    if (rc) return rc;
+    MMIF_CUDA(cudaMemcpyAsync(out_host, dev_out, (size_t)N * MMIF_EVAL_METRICS * 8, cudaMemcpyDeviceToHost, st));
+    MMIF_CUDA(cudaStreamSynchronize(st));
+    return MMIF_OK;
+}
+
 extern "C" int mmif_tv_loss(const float* x, int N, int H, int W, int norm, float weight, double* out, void* ws, size_t ws_bytes,
                             void* stream) {
     if (!x || !out) { set_error("null pointer"); return MMIF_E_NULL; }

@@ -60,6 +60,7 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
     p.pixel_norm = L.cfg.pixel_norm; p.grad_norm = L.cfg.grad_norm;
     p.w_ssim = L.cfg.w_ssim; p.w_pixel = L.cfg.w_pixel; p.w_grad = L.cfg.w_grad;
     p.do_sobel = L.do_sobel;
+    for (int i = 0; i < 6; ++i) p.maps[i] = L.maps[i];
     unsigned char* w8 = (unsigned char*)ws;
     p.fin.B = B; p.fin.H = H; p.fin.W = W; p.fin.Hout = g.Hout; p.fin.Wout = g.Wout;
     p.fin.finalize = L.finalize;
@@ -73,6 +74,7 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
     if (!p.use_tma) { memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2)); memset(&my, 0, sizeof(my)); }
     dim3 grid(g.nstrip, g.nseg, B);
     if (L.epi == EPI_SSIM && L.win == 11) return launch_t<11, EPI_SSIM>(m1, m2, my, p, grid, st);
+    if (L.epi == EPI_MAPS && L.win == 11) return launch_t<11, EPI_MAPS>(m1, m2, my, p, grid, st);
     if (L.epi == EPI_VIF) {
         switch (L.win) {
             case 17: return launch_t<17, EPI_VIF>(m1, m2, my, p, grid, st);

@@ -12,7 +12,7 @@
 
 namespace mmif {
 
-enum { EPI_SSIM = 0, EPI_VIF = 1, EPI_MSW = 2 };
+enum { EPI_SSIM = 0, EPI_VIF = 1, EPI_MSW = 2, EPI_MAPS = 3 };
 enum { FIN_SUMS = 0, FIN_LOSS = 1 };
 
 // TMA needs the global address of a box (innermost coordinate * 4 B) 16-byte aligned, so strips
@@ -108,6 +108,7 @@ struct FwdParams {
     float w_ssim, w_pixel, w_grad;
     int use_tma;
     int do_sobel;            // EPI_SSIM only: also accumulate the Sobel / pixel terms
+    float* maps[6];          // EPI_MAPS: [ssim1, cs1, sigma1, ssim2, cs2, sigma2] maps [B][Hout][Wout] (each may be NULL)
 };
 
 static inline size_t ws_counters_bytes(int B) { return (size_t)(((B + 1) * 4 + 255) / 256) * 256; }
@@ -292,6 +293,19 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
                         const float sg1 = fmaxf(vk.x, 1e-4f), sg2 = fmaxf(vk.y, 1e-4f);
                         const float gm = __fdiv_rn(sg1, fmaxf(sg1 + sg2, 1e-7f));
                         s0 = add2(s0, f2(gm * S.x + (1.f - gm) * S.y, 0.f));
+                    } else if (EPI == EPI_MAPS) {       // size_average=False: the maps themselves (loss.py:99-108)
+                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
+                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
+                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
+                        const float2 B2 = add2(vk, bcast(vy + p.C2));
+                        const float2 S = fdiv_nr2(mul2(A1, A2), mul2(B1, B2)), CS = fdiv_nr2(A2, B2), SG = max2(vk, 1e-4f);
+                        const size_t o = ((size_t)n * p.Hout + (i0 + b * kRB + ho)) * p.Wout + (j0 + hg * 8 + j);
+                        if (p.maps[0]) p.maps[0][o] = S.x;
+                        if (p.maps[1]) p.maps[1][o] = CS.x;
+                        if (p.maps[2]) p.maps[2][o] = SG.x;
+                        if (p.maps[3]) p.maps[3][o] = S.y;
+                        if (p.maps[4]) p.maps[4][o] = CS.y;
+                        if (p.maps[5]) p.maps[5][o] = SG.y;
                     } else if (EPI == EPI_SSIM) {
                         const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
                         const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
@@ -351,6 +365,7 @@ struct FwdLaunch {
     int do_sobel;
     float data_range;
     MmifLossCfg cfg;         // combine / norm / weights (EPI_SSIM + do_sobel)
+    float* maps[6];          // EPI_MAPS outputs
 };
 int fwd_seg_rows(int rows, int other_ctas);
 size_t fwd_ws_bytes(int win, int B, int H, int W);       // counters + partials (sums live elsewhere)

@@ -121,7 +121,9 @@ def test_errors_match_reference():
         ML.PixelLoss('l3')(x, x, x, mode='max')
     assert ML.PixelLoss('l1')(x, x, x, mode='other') is None
     with pytest.raises(NotImplementedError):
-        ML.SSIM(size_average=False)(x, x)
+        ML.SSIM(win_size=7)(x, x)                        # only the 11-tap window of the objective is built
+    with pytest.raises(NotImplementedError):
+        ML.SSIMLoss('ssim')(x.clone().requires_grad_(True), x, x)   # gradients w.r.t. the sources
     with pytest.raises(Exception):
         ML.SSIMLoss('ssim')(x.cpu(), x.cpu(), x.cpu())   # no CPU fallback
 
@@ -250,3 +252,53 @@ def test_msw_ssim_forward_backward():
         a, b, f = (T(x) for x in cases.loss_case(name))
         _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('msw-ssim', weight=1.3)(x1, x2, y),
                         lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'msw-ssim', weight=1.3), a, b, f)
+
+
+def test_ms_ssim_with_padding_pads_every_level():
+    ML = _mods()
+    g = torch.Generator().manual_seed(8)
+    a, b, f = (torch.rand(2, 1, 93, 120, generator=g) for _ in range(3))     # 93 -> 47 -> 24 -> 12 -> 6 (valid windows would fail)
+    f = (0.5 * (a + b) + 0.1 * f).contiguous()
+    _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('ms-ssim', use_padding=True)(x1, x2, y),
+                    lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'ms-ssim', use_padding=True), a, b, f)
+    ms = ML.MS_SSIM(use_padding=True)(a.cuda(), f.cuda())
+    ref = OL.msssim(a, f, window=OL.window2d(11, 1.5), data_range=1.0, use_padding=True)
+    ref64 = OL.msssim(a.double(), f.double(), window=OL.window2d(11, 1.5).double(), data_range=1.0, use_padding=True)
+    for k in range(2):       # a product of five level values: the reference's own fp32 noise reaches 1e-5 here
+        gates.assert_scalar(f'ms_ssim_pad[{k}]', ms[k].item(), ref[k].item(), ref64[k].item())
+
+
+def test_msw_ssim_with_padding():
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_2x40x37'))
+    _grad_vs_oracle(lambda x1, x2, y: ML.SSIMLoss('msw-ssim', use_padding=True)(x1, x2, y),
+                    lambda x1, x2, y: OL.ssim_loss(x1, x2, y, 'msw-ssim', use_padding=True), a, b, f)
+
+
+def test_ssim_maps_and_auto_range():
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_2x40x37'))
+    d = ML.SSIM(size_average=False, data_range=None)(a.cuda(), f.cuda())
+    ref = OL.ssim(a.double(), f.double(), window=OL.window2d(11, 1.5).double(), data_range=None, size_average=False)
+    for key in ('ssim', 'cs', 'sigma'):
+        assert tuple(d[key].shape) == tuple(ref[key].shape)
+        np.testing.assert_allclose(d[key].cpu().numpy(), ref[key].numpy(), rtol=2e-5, atol=2e-6)
+    big = (a * 255.0)
+    l_new = ML.SSIMLoss('ssim', data_range=None)(big.cuda(), (b * 255.0).cuda(), (f * 255.0).cuda()).item()
+    l_ref = OL.ssim_loss(big, b * 255.0, f * 255.0, 'ssim', data_range=None).item()
+    assert abs(l_new - l_ref) <= 1e-5 * abs(l_ref) + 1e-7
+
+
+@pytest.mark.parametrize('mode', ['l1', 'l2'])
+def test_norm_loss_forward_backward(mode):
+    ML = _mods()
+    g = torch.Generator().manual_seed(2)
+    x = (torch.rand(3, 2, 33, 65, generator=g) - 0.5)
+    xg = x.cuda().requires_grad_(True)
+    l = ML.NormLoss(mode, weight=0.4)(xg)
+    gx, = torch.autograd.grad(l, xg)
+    xd = x.double().requires_grad_(True)
+    l64 = OL.norm_loss(xd, mode, 0.4)
+    g64, = torch.autograd.grad(l64, xd)
+    assert abs(l.item() - l64.item()) <= 1e-6 * abs(l64.item())
+    np.testing.assert_allclose(gx.cpu().numpy(), g64.numpy(), rtol=1e-6, atol=1e-12)

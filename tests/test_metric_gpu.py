@@ -179,3 +179,33 @@ def test_histogram_counter_overflow_and_split_modes(n_pairs):
             gates.assert_scalar(f'ovf/nmi{k}', ent[n, 9 + k], r32, r64)
             gates.assert_scalar(f'ovf/ce{k}', ent[n, 5 + k], OM.cross_entropy(x, y).item(), OM.cross_entropy(x.double(), y.double()).item())
         gates.assert_scalar('ovf/en_f', ent[n, 2], OM.entropy(fn).item(), OM.entropy(fn.double()).item())
+
+
+def test_use_padding_and_maps_vs_oracle():
+    """calc_ssim / calc_msssim with use_padding=True (reflect pad per level) and size_average=False (maps)."""
+    MM = _mods()
+    g = torch.Generator().manual_seed(21)
+    a = torch.randint(0, 256, (1, 1, 90, 117), generator=g).float()
+    f = torch.floor(0.5 * (a + torch.randint(0, 256, (1, 1, 90, 117), generator=g).float()))
+    for fn_new, fn_ref in ((MM.calc_ssim, OM.ssim), (MM.calc_msssim, OM.msssim)):
+        got = fn_new(a.cuda(), f.cuda(), use_padding=True).item()
+        gates.assert_scalar(fn_ref.__name__ + '/pad', got, fn_ref(a, f, use_padding=True).item(),
+                            fn_ref(a.double(), f.double(), use_padding=True).item())
+    for pad in (False, True):
+        s_map, cs_map = MM.calc_ssim(a.cuda(), f.cuda(), use_padding=pad, size_average=False, full=True)
+        r_s, r_cs = OM.ssim(a.double(), f.double(), use_padding=pad, size_average=False, full=True)
+        assert tuple(s_map.shape) == tuple(r_s.shape)
+        np.testing.assert_allclose(s_map.cpu().numpy(), r_s.numpy(), rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(cs_map.cpu().numpy(), r_cs.numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_uint8_ingest_equals_float_path():
+    MM = _mods()
+    g = torch.Generator().manual_seed(4)
+    a = torch.randint(0, 256, (3, 1, 131, 203), generator=g, dtype=torch.uint8)
+    b = torch.randint(0, 256, (3, 1, 131, 203), generator=g, dtype=torch.uint8)
+    f = torch.maximum(a, b)
+    ref = MM.eval_metrics_batch(a.float().cuda(), b.float().cuda(), f.float().cuda())
+    for src in ((a, b, f), (a.cuda(), b.cuda(), f.cuda()), (a.pin_memory(), b.pin_memory(), f.pin_memory())):
+        got = MM.eval_metrics_batch_u8(*src)
+        assert torch.equal(got, ref)
