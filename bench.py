@@ -241,7 +241,8 @@ def main():
                 'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
                 'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
                 'ms_per_launch': ms_z,
-                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/): the pipe roof is ~58 Gpix/s'}
+                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/r1d_zkernel.txt: FMA pipe 61% active, '
+                        'DRAM 8%): 1056 packed FMAs per 8 output pixels put the pipe roof of this kernel at ~64 Gpix/s'}
     two_kernel = {'value': total_mpix / (ms_step2 * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step2,
                   'fwd': {'kernel': 'moment_fwd_kernel<11,EPI_SSIM>', 'ms_per_launch': ms_fwd, 'achieved': gbs(ALG_BYTES_FWD, ms_fwd),
                           'frac': gbs(ALG_BYTES_FWD, ms_fwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_FWD},
@@ -336,26 +337,59 @@ def e2e_leg(args, dev, world, rank, ML, B):
 
 
 def metric_suite_leg(dev, MM):
-    """Second headline metric: full 16-metric suite, pairs/s (BASELINE configs[2] and configs[3] shapes)."""
+    """Second headline metric: full 16-metric suite, pairs/s (BASELINE configs[2] and configs[3] shapes).
+    `pairs_per_s`: images resident in HBM (float32, as the reference's functions take them);
+    `e2e_*`: through the public batched entry with HOST buffers, H2D of the images and D2H of the rows inside
+    the timed region — float32 host images (what eval.py builds, eval.py:189-194) and uint8 host images
+    (what cv2 decodes, eval.py:182-187; widened on the device);
+    `cpu_reference_pairs_per_s`: the oracle port of eval.py:29-75 on the host cores, one pair."""
+    from oracle import fusion_metric as OM
     out = {}
+    peak = measured_peak()[0]
     for name, (n, h, w) in (('tno_21x640x480', (21, 480, 640)), ('polar_32x1224x1024', (32, 1024, 1224))):
         g = torch.Generator(device=dev).manual_seed(7)
         a = torch.randint(0, 256, (n, 1, h, w), device=dev, generator=g).float()
         b = torch.randint(0, 256, (n, 1, h, w), device=dev, generator=g).float()
         f = torch.floor((a + b) / 2)
-        for _ in range(3):
-            MM.eval_metrics_batch(a, b, f)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 10
-        e0.record()
-        for _ in range(iters):
-            MM.eval_metrics_batch(a, b, f)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+
+        def timeit(fn, iters):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        ms = timeit(lambda: MM.eval_metrics_batch(a, b, f), 10)
+        hf = [t.cpu().pin_memory() for t in (a, b, f)]
+        hu = [t.to(torch.uint8).cpu().pin_memory() for t in (a, b, f)]
+        rows_host = torch.empty(n, 16, dtype=torch.float64).pin_memory()
+
+        def e2e_f32():
+            d = [t.to(dev, non_blocking=True) for t in hf]
+            rows_host.copy_(MM.eval_metrics_batch(*d), non_blocking=True)
+            torch.cuda.synchronize()
+
+        def e2e_u8():
+            rows_host.copy_(MM.eval_metrics_batch_u8(*hu), non_blocking=True)
+            torch.cuda.synchronize()
+
+        ms_f32, ms_u8 = timeit(e2e_f32, 5), timeit(e2e_u8, 5)
+        ca, cb, cf_ = (t[:1].cpu() for t in (a, b, f))
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        OM.eval_pair(ca, cb, cf_)
+        cpu_s = time.perf_counter() - t0
         out[name] = {'pairs_per_s': n / (ms * 1e-3), 'ms_per_batch': ms, 'pairs': n,
-                     'hbm_frac_87.6B_per_pixel': 87.6 * n * h * w / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+                     'hbm_frac_87.6B_per_pixel': 87.6 * n * h * w / (ms * 1e-3) / 1e9 / peak,
+                     'e2e_f32_host_pairs_per_s': n / (ms_f32 * 1e-3), 'e2e_u8_host_pairs_per_s': n / (ms_u8 * 1e-3),
+                     'h2d_bytes_f32': 12 * n * h * w, 'h2d_bytes_u8': 3 * n * h * w, 'd2h_bytes': n * 16 * 8,
+                     'cpu_reference_pairs_per_s': 1.0 / cpu_s, 'cpu_cores': torch.get_num_threads(),
+                     'cpu_sample': '1 pair, oracle port of eval.py:29-75, single run'}
     return out
 
 

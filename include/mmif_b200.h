@@ -147,6 +147,13 @@ int mmif_ssim_maps(const float* i1, const float* i2, const float* f, int B, int 
                    float* ssim1, float* cs1, float* sigma1, float* ssim2, float* cs2, float* sigma2,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* test.py:49-73 post-step in one pass over imgf: out = the loss block of mmif_fusion_loss_fwd
+ * (mmif_loss_out_doubles(B) doubles; per sample ssim1, cs1, sigma1, ssim2, cs2, sigma2 = calc_ssim(i1, f) and
+ * calc_ssim(i2, f) with `data_range`, test.py:51-52) and, if denorm_u8 != NULL, the image save_result / denorm write
+ * (common.py:74-81, data/transform.py:32-35): uint8(clip(f, 0, 1) * 255) as [B][H][W] bytes. */
+int mmif_test_post(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
+                   double* out, unsigned char* denorm_u8, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- metric suite ----------- */
 /* All metric entries are batched over N independent pairs (a[n], b[n], f[n]) of one shape and
  * write doubles per pair.  ws from mmif_metric_workspace_bytes. */

@@ -374,6 +374,30 @@ def eval_metrics_batch(img1, img2, imgf):
     return _call('mmif_eval_suite', imgs, shape, L.EVAL_METRICS)
 
 
+def test_post_step(img1, img2, imgf, data_range=1.0, want_image=True):
+    """test.py:49-73 after the model call, in one launch and one pass over imgf:
+    ``(ssim1 + ssim2) * 0.5`` with ``ssim_k = calc_ssim(img_k, imgf, data_range=1.0)`` per sample -> (B,) float32
+    tensor, and ``save_result(imgf[b])`` = ``denorm`` (uint8(clip(0,1)*255), data/transform.py:32-35) -> (B,H,W) uint8
+    device tensor (``.cpu().numpy()[b][..., None]`` is what cv2.imwrite gets in test.py:72-73)."""
+    lib = L.load()
+    for t in (img1, img2, imgf):
+        L.require_cuda(t, 'image')
+    imgs, (n, h, w), _ = _prep(img1, img2, imgf)
+    dev = imgs[0].device
+    nws = lib.mmif_loss_workspace_bytes(n, h, w)
+    if nws == 0:
+        raise L.MmifError(f'unsupported shape {(n, h, w)}: H and W must be >= 11')
+    ws = L.workspace(dev, nws, 'loss', (n, h, w))
+    out = torch.empty(lib.mmif_loss_out_doubles(n), dtype=torch.float64, device=dev)
+    img8 = torch.empty(n, h, w, dtype=torch.uint8, device=dev) if want_image else None
+    with torch.cuda.device(dev):
+        L.check(lib.mmif_test_post(imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, float(data_range),
+                                   out.data_ptr(), img8.data_ptr() if want_image else None, ws.data_ptr(), ws.numel(),
+                                   L.stream_ptr(dev)))
+    ps = out[L.LOSS_HEAD:].view(n, L.LOSS_PER_SAMPLE)
+    return ((ps[:, 0] + ps[:, 3]) * 0.5).to(torch.float32), img8
+
+
 def eval_metrics_batch_u8(img1, img2, imgf):
     """uint8 ingest: (N,1,H,W) / (N,H,W) uint8 tensors — CUDA, or pinned / pageable HOST tensors (one H2D copy of
     1 byte per pixel per image) -> (N,16) float64 rows on the GPU.  Same results as widening on the host

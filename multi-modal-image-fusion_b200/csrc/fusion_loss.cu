@@ -618,6 +618,25 @@ extern "C" int mmif_ssim_maps(const float* i1, const float* i2, const float* f, 
     return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, nullptr, ws, core, (cudaStream_t)stream);
 }
 
+/* test.py:49-73 post-step in ONE pass over imgf: the per-sample SSIM of (i1, f) and (i2, f) (calc_ssim with data_range,
+ * test.py:51-52) and the 8-bit image save_result / denorm write (common.py:74-81, data/transform.py:32-35). */
+extern "C" int mmif_test_post(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
+                              double* out, unsigned char* denorm_u8, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_common(i1, i2, f, B, H, W);
+    if (rc) return rc;
+    if (!out) { set_error("null out"); return MMIF_E_NULL; }
+    if (!ws || ws_bytes < mmif_loss_workspace_bytes(B, H, W)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
+    const size_t core = loss_ws_core_bytes(B, H, W);
+    FwdLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.win = WIN11; L.sigma = 1.5; L.epi = EPI_SSIM; L.finalize = FIN_LOSS; L.do_sobel = 1; L.data_range = data_range;
+    L.cfg.w_ssim = 1.f; L.cfg.w_pixel = 1.f; L.cfg.w_grad = 1.f; L.cfg.data_range = data_range;
+    L.cfg.pixel_combine = L.cfg.grad_combine = MMIF_COMBINE_MAX; L.cfg.pixel_norm = L.cfg.grad_norm = MMIF_NORM_L1;
+    L.denorm = denorm_u8;
+    double* sums = (double*)((unsigned char*)ws + core);
+    return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, out, ws, core, (cudaStream_t)stream);
+}
+
 static double loss_sigma_of(int win) { return win == 11 ? 1.5 : 0.15 * (win - 1); }     // loss.py:34
 static bool msw_win_ok(int win) { return win == 11 || win == 9 || win == 7 || win == 5 || win == 3; }
 

@@ -61,6 +61,7 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
     p.w_ssim = L.cfg.w_ssim; p.w_pixel = L.cfg.w_pixel; p.w_grad = L.cfg.w_grad;
     p.do_sobel = L.do_sobel;
     for (int i = 0; i < 6; ++i) p.maps[i] = L.maps[i];
+    p.denorm = L.denorm;
     unsigned char* w8 = (unsigned char*)ws;
     p.fin.B = B; p.fin.H = H; p.fin.W = W; p.fin.Hout = g.Hout; p.fin.Wout = g.Wout;
     p.fin.finalize = L.finalize;

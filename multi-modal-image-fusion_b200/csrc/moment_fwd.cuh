@@ -109,6 +109,7 @@ struct FwdParams {
     int use_tma;
     int do_sobel;            // EPI_SSIM only: also accumulate the Sobel / pixel terms
     float* maps[6];          // EPI_MAPS: [ssim1, cs1, sigma1, ssim2, cs2, sigma2] maps [B][Hout][Wout] (each may be NULL)
+    unsigned char* denorm;   // do_sobel: also store uint8(clip(y, 0, 1) * 255) [B][H][W] (test.py:70-73 post-step) or NULL
 };
 
 static inline size_t ws_counters_bytes(int B) { return (size_t)(((B + 1) * 4 + 255) / 256) * 256; }
@@ -154,6 +155,10 @@ __device__ __forceinline__ void fwd_sobel_pixel(const SM& sm, const FwdParams& p
                 pix_sum += norm_val(u0[2] - fmaxf(u0[0], u0[1]), p.pixel_norm);
             } else {
                 pix_sum += 0.5f * (norm_val(u0[2] - u0[0], p.pixel_norm) + norm_val(u0[2] - u0[1], p.pixel_norm));
+            }
+            if (p.denorm) {      // denorm() of data/transform.py:32-35: clip(0,1) * 255 in float32, truncated to uint8 (NaN -> 0)
+                const float v = fminf(fmaxf(u0[2], 0.f), 1.f) * 255.0f;
+                p.denorm[((size_t)blockIdx.z * p.H + (r - 1)) * p.W + c] = (unsigned char)__float2uint_rz(v);
             }
         }
     }
@@ -261,7 +266,7 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
     constexpr float kVifEps = 1e-10f, kVifNoise = 325.125f;            // metric.py:407-408
 
     const bool fast_terms = p.pixel_combine == MMIF_COMBINE_MAX && p.grad_combine == MMIF_COMBINE_MAX &&
-                            p.pixel_norm == MMIF_NORM_L1 && p.grad_norm == MMIF_NORM_L1;
+                            p.pixel_norm == MMIF_NORM_L1 && p.grad_norm == MMIF_NORM_L1 && p.denorm == nullptr;
     for (int b = 0; b < nb; ++b) {
         ring_wait(sm, src, b + 2);
         vpass_moments<WIN>(sm, p.taps, sh, (b % 3) * kRB);
@@ -366,6 +371,7 @@ struct FwdLaunch {
     float data_range;
     MmifLossCfg cfg;         // combine / norm / weights (EPI_SSIM + do_sobel)
     float* maps[6];          // EPI_MAPS outputs
+    unsigned char* denorm;   // do_sobel: uint8 image of y (or NULL)
 };
 int fwd_seg_rows(int rows, int other_ctas);
 size_t fwd_ws_bytes(int win, int B, int H, int W);       // counters + partials (sums live elsewhere)

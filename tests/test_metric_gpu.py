@@ -209,3 +209,23 @@ def test_uint8_ingest_equals_float_path():
     for src in ((a, b, f), (a.cuda(), b.cuda(), f.cuda()), (a.pin_memory(), b.pin_memory(), f.pin_memory())):
         got = MM.eval_metrics_batch_u8(*src)
         assert torch.equal(got, ref)
+
+
+def test_test_py_post_step_one_pass():
+    """test.py:49-73: avg SSIM (data_range=1.0) and the denorm() image; the image must be bit-exact."""
+    MM = _mods()
+    g = torch.Generator().manual_seed(12)
+    a, b = (torch.rand(2, 1, 75, 133, generator=g) for _ in range(2))
+    f = (0.5 * (a + b) + 0.4 * (torch.rand(2, 1, 75, 133, generator=g) - 0.5)) * 1.3 - 0.1      # leaves [0, 1]: the clip matters
+    f[0, 0, 3, 5] = float('nan'); f[1, 0, 0, 0] = 1.0; f[1, 0, 74, 132] = 0.999999
+    f_ok = torch.nan_to_num(f, nan=0.5)
+    ssim, img8 = MM.test_post_step(a.cuda(), b.cuda(), f_ok.cuda())
+    for n in range(2):
+        r32 = ((OM.ssim(a[n:n + 1], f_ok[n:n + 1], data_range=1.0) + OM.ssim(b[n:n + 1], f_ok[n:n + 1], data_range=1.0)) * 0.5).item()
+        r64 = ((OM.ssim(a[n:n + 1].double(), f_ok[n:n + 1].double(), data_range=1.0) +
+                OM.ssim(b[n:n + 1].double(), f_ok[n:n + 1].double(), data_range=1.0)) * 0.5).item()
+        gates.assert_scalar('test_post/ssim', ssim[n].item(), r32, r64)
+        ref8 = (f_ok[n].numpy().clip(0, 1) * 255.0).transpose((1, 2, 0)).astype(np.uint8)[..., 0]      # data/transform.py:32-35
+        assert np.array_equal(img8[n].cpu().numpy(), ref8)
+    _, img8n = MM.test_post_step(a.cuda(), b.cuda(), f.cuda())
+    assert int(img8n[0, 3, 5]) == 0 and np.array_equal(img8n[1].cpu().numpy(), img8[1].cpu().numpy())
