@@ -28,7 +28,7 @@ def _make_dataset(tmp, n=7, seed=0):
     names = [f'{i}.png' for i in range(1, n + 1)]             # 1.png ... 10.png: natural order != lexicographic
     arrays = {}
     for k, name in enumerate(sorted(names, key=lambda s: int(s.split('.')[0]))):
-        shape = (48, 64) if k % 3 else (40, 72)
+        shape = (96, 128) if k % 3 else (80, 144)
         a = rng.integers(0, 256, shape, dtype=np.uint8)
         b = rng.integers(0, 256, shape, dtype=np.uint8)
         f = np.maximum(a, b)
