@@ -90,6 +90,14 @@ __device__ __forceinline__ float fdiv_nr(float a, float b) {
 }
 __device__ __forceinline__ float2 fdiv_nr2(float2 a, float2 b) { return f2(fdiv_nr(a.x, b.x), fdiv_nr(a.y, b.y)); }
 
+// 1/b by MUFU.RCP alone (max relative error 2^-23): for quantities whose consumers tolerate one more ulp
+__device__ __forceinline__ float rcp_approx(float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 rcp2(float2 b) { return f2(rcp_approx(b.x), rcp_approx(b.y)); }
+
 __device__ __forceinline__ float finite_or_zero(float v) { return (fabsf(v) <= 3.0e38f) ? v : 0.0f; }
 
 // ----------------------------------------------------------------------------- reductions

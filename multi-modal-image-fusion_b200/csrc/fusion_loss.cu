@@ -120,7 +120,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         return;
     }
     const float npx = (float)p.B * (float)p.H * (float)p.W;
-    const float k_ssim = g_ssim * p.ssim_base / ((float)p.Hout * (float)p.Wout);
+    const float k_ssim2 = 2.f * g_ssim * p.ssim_base / ((float)p.Hout * (float)p.Wout);   // the blurred coefficients are halved
     const float2 pairw = (EXT && p.pair_w) ? f2(__ldg(p.pair_w + 2 * n), __ldg(p.pair_w + 2 * n + 1)) : f2(1.f, 1.f);
     const float k_pix = g_pix * p.w_pixel / npx * (p.pixel_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
     const float k_grad = g_grad * p.w_grad / npx * (p.grad_combine == MMIF_COMBINE_MAX ? 1.f : 0.5f);
@@ -151,12 +151,29 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     const int s_t0 = min(s_cc - jw0, kRPB - 1);
     const int s_tm = min(((s_cc == 0) ? 1 : s_cc - 1) - jw0, kRPB - 1);
     const int s_tp = min(((s_cc == p.W - 1) ? p.W - 2 : s_cc + 1) - jw0, kRPB - 1);
+    // fast-path constants: ring pointer of the thread's column, ownership as a factor
+    constexpr int kRingImg = SmemB::kRows * kRPB;
+    // (strips whose Sobel columns j0-1 .. j0+kTG all lie in [2, W-3]: no column reflection or folding)
+    const bool s_strip_int = (j0 >= 3) && (j0 + kTG <= p.W - 3);
+    const float* s_p0 = &sm.ring[0][0][min(max(s_c - jw0, 1), kRPB - 2)];
+    const float s_ownf = s_own ? 1.f : 0.f;
+    float* s_gdst = &sb.gbuf[0][s_own ? s_ci : kTMC];
     float2 s_dA = f2(0.f, 0.f), s_dB = s_dA, s_sA = s_dA, s_sB = s_dA, s_ucA = s_dA, s_ucB = s_dA;
     float s_dAy = 0.f, s_dBy = 0.f, s_sAy = 0.f, s_sBy = 0.f, s_ucAy = 0.f, s_ucBy = 0.f;
     float s_hxA = 0.f, s_hxB = 0.f, s_vyA = 0.f, s_vyB = 0.f;
     float2 z_ss = f2(0.f, 0.f), z_cs = z_ss, z_sg = z_ss;     // ZMODE loss accumulators
     float z_pix = 0.f, z_grad = 0.f;
 
+    // window columns of this thread's H-pass group: bit j of a_vmask = column carries a valid window,
+    // of a_zmask = ... and its SSIM value belongs to this CTA's tile (single-pass loss sums)
+    unsigned a_vmask = 0u, a_zmask = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int pw = hg * 8 + j, pc = jw0 + pw;
+        const bool v = (pw < kWC) && (pc >= 0) && (pc < p.Wout);
+        a_vmask |= v ? (1u << j) : 0u;
+        a_zmask |= (v && pc >= j0 && pc < jend) ? (1u << j) : 0u;
+    }
     for (int b = 0; b < nb; ++b) {
         const int Rb = R0 + b * kRB;                  // first gradient row of this batch
         ring_wait(sm, src, b + 2);
@@ -166,7 +183,45 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         // thread = column (warps own 30 columns + 1 halo lane each side); one input row per step:
         // input row q' -> Sobel / tx,ty of row q'-1 -> (neighbour columns by shuffle) -> G of row q'-2.
         // All sliding state lives in registers across batches, so every input row is visited once.
-        if (!EXT && p.do_sobel) {
+        // Interior batches (no row reflection / folding, every row owned, 'max' + 'l1'): branch-free,
+        // fully unrolled — the sliding state is renamed instead of moved, borders cost nothing.
+        const bool s_fast = FAST && !EXT && p.do_sobel && s_strip_int && (Rb >= max(2, i0)) && (Rb + 9 <= min(iend, p.H - 1));
+        if (s_fast) {
+            const int bb = (b & 3) * kRB + 2;
+#pragma unroll
+            for (int step = 0; step < kRB; ++step) {
+                const int lro = ((bb + step) & (SmemB::kRows - 1)) * kRPB;      // ring row of input row Rb + 2 + step
+                const float* rp = s_p0 + lro;
+                const float2 um = f2(rp[-1], rp[kRingImg - 1]);
+                const float2 uc = f2(rp[0], rp[kRingImg]);
+                const float2 up = f2(rp[1], rp[kRingImg + 1]);
+                const float umy = rp[2 * kRingImg - 1], ucy = rp[2 * kRingImg], upy = rp[2 * kRingImg + 1];
+                const float2 d = fma2(bcast(-1.f), um, up);
+                const float2 sv = fma2(bcast(2.f), uc, add2(um, up));
+                const float2 gx = fma2(bcast(2.f), s_dB, add2(s_dA, d));   // Sobel of row Rb + 1 + step
+                const float2 gy = fma2(bcast(-1.f), s_sA, sv);
+                const float dy = upy - umy;
+                const float sy = fmaf(2.f, ucy, umy + upy);
+                const float gxy = fmaf(2.f, s_dBy, s_dAy + dy);
+                const float gyy = sy - s_sAy;
+                const float S1 = fabsf(gx.x) + fabsf(gy.x), S2 = fabsf(gx.y) + fabsf(gy.y), Sy = fabsf(gxy) + fabsf(gyy);
+                const float D = Sy - fmaxf(S1, S2);
+                const float r = mulsign(k_grad, D);
+                const float tx = mulsign(r, gxy), ty = mulsign(r, gyy);
+                if (ZMODE) z_grad = fmaf(s_ownf, fabsf(D), z_grad);
+                const float txl = __shfl_up_sync(0xffffffffu, tx, 1), txr = __shfl_down_sync(0xffffffffu, tx, 1);
+                const float tyl = __shfl_up_sync(0xffffffffu, ty, 1), tyr = __shfl_down_sync(0xffffffffu, ty, 1);
+                const float hx = txl - txr;
+                const float vy = fmaf(2.f, ty, tyl + tyr);
+                const float dp = s_ucAy - fmaxf(s_ucA.x, s_ucA.y);
+                const float G = (s_hxA + s_vyA) + fmaf(2.f, s_hxB, hx - vy) + mulsign(k_pix, dp);
+                s_gdst[step * (kTMC + 4)] = G;                             // lanes that own no column write a pad column
+                if (ZMODE) z_pix = fmaf(s_ownf, fabsf(dp), z_pix);
+                s_dA = s_dB; s_dB = d; s_sA = s_sB; s_sB = sv; s_dAy = s_dBy; s_dBy = dy; s_sAy = s_sBy; s_sBy = sy;
+                s_hxA = s_hxB; s_hxB = hx; s_vyA = s_vyB; s_vyB = vy;
+                s_ucA = s_ucB; s_ucB = uc; s_ucAy = s_ucBy; s_ucBy = ucy;
+            }
+        } else if (!EXT && p.do_sobel) {
 #pragma unroll 2
             for (int step = 0; step < kRB; ++step) {
                 const int qp = Rb + 2 + step;                       // input row q'
@@ -234,58 +289,58 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
             if (active) {
                 float2 acc[8][4];
                 hpass<WIN, 4, false>(sm.vbuf + ho * kVPitch + hg * 8, kVCols, p.taps, acc);
+                const unsigned zm = (ZMODE && q >= i0 && q < iend) ? a_zmask : 0u;
+                // Branch-free over the 8 window columns (independent chains interleave); columns without a
+                // valid window are computed on zero-filled data (finite) and masked at the end.
+                // Stored coefficients: ab = (a/2, -b), cc = c/2 with a = dS/dmu_y', b = dS/dE[y'^2], c = dS/dE[x'y'].
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int pw = hg * 8 + j;
-                    const int pc = jw0 + pw;
-                    ab[j] = cc[j] = f2(0.f, 0.f);
-                    if (pw < kWC && pc >= 0 && pc < p.Wout) {
-                        const Moments mo = moments_of(acc[j]);
-                        const Stats st = stats_from(mo, sh);
-                        const float myk = (st.vy >= 0.f) ? 1.f : 0.f;
-                        const float2 vk = max2(st.vk, 0.f);
-                        const float vy = fmaxf(st.vy, 0.f);
-                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
-                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
-                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
-                        const float2 B2 = add2(vk, bcast(vy + p.C2));
-                        const float2 rB1 = fdiv_nr2(bcast(1.f), B1);
-                        const float2 rB2 = fdiv_nr2(bcast(1.f), B2);
-                        const float2 rBB = mul2(rB1, rB2);
-                        float2 S, dcov, dvar, dmu;
-                        if (EXT && p.cs_only) {                                          // S = cs = A2 / B2
-                            S = mul2(A2, rB2);
-                            dcov = muls(2.f, rB2);
-                            dvar = muls(-myk, mul2(S, rB2));
-                            dmu = f2(0.f, 0.f);
-                        } else {
-                            S = mul2(mul2(A1, A2), rBB);
-                            dcov = mul2(muls(2.f, A1), rBB);                             // dS/dcov
-                            dvar = muls(-myk, mul2(S, rB2));                             // dS/dvar_y
-                            // dS/dmu_y (luminance path) = 2 mu_k A2/(B1 B2) - 2 mu_y S / B1
-                            dmu = fma2(mul2(muls(2.f, st.mu), A2), rBB, muls(-2.f * st.muy, mul2(S, rB1)));
-                        }
-                        // a' = dmu - dvar (2 my' + 2 eps cy) - dcov (mk' + eps ck)
-                        const float2 a = fma2(muls(-1.f, dcov), add2(mo.mk, sh.ec),
-                                              fma2(muls(-1.f, dvar), bcast(2.f * mo.my + sh.k1y), dmu));
+                    const Moments mo = moments_of(acc[j]);
+                    const Stats st = stats_from(mo, sh);
+                    const float myk = (st.vy >= 0.f) ? 1.f : 0.f;        // clamp(min=0) passes the gradient at 0
+                    const float2 vk = max2(st.vk, 0.f);
+                    const float vy = fmaxf(st.vy, 0.f);
+                    const float2 A1 = fma2(st.mu, bcast(2.f * st.muy), bcast(p.C1));
+                    const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
+                    const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
+                    const float2 B2 = add2(vk, bcast(vy + p.C2));
+                    const float2 R1 = rcp2(B1), R2 = rcp2(B2);
+                    const float2 Cs = mul2(A2, R2);
+                    float2 S, ch, nb, a;
+                    if (EXT && p.cs_only) {                                          // S = cs = A2 / B2
+                        S = Cs;
+                        ch = R2;
+                        nb = muls(myk, mul2(S, R2));
+                        a = f2(0.f, 0.f);
+                    } else {
+                        const float2 L = mul2(A1, R1);
+                        S = mul2(L, Cs);
+                        ch = mul2(L, R2);                                            // (dS/dcov) / 2 = A1 / (B1 B2)
+                        nb = muls(myk, mul2(S, R2));                                 // -dS/dvar_y = S / B2
+                        a = mul2(mul2(Cs, R1), fma2(L, bcast(-st.muy), st.mu));      // (dS/dmu_y) / 2 = Cs / B1 (mu_k - mu_y L)
+                    }
+                    // a/2 = (dS/dmu_y)/2 - dS/dvar_y (my' + eps cy) - (dS/dcov)/2 (mk' + eps ck)
+                    a = fma2(nb, bcast(mo.my + sh.ecy), a);
+                    a = fma2(ch, fma2(mo.mk, bcast(-1.f), sh.nec), a);
+                    const bool vj = (a_vmask >> j) & 1u;
+                    if (EXT) {
                         float2 wq = pairw;
-                        if (EXT && p.msw) {                                                     // gamma = sigma1 / (sigma1 + sigma2), loss.py:232-233
+                        if (p.msw) {                                                    // gamma = sigma1 / (sigma1 + sigma2), loss.py:232-233
                             const float sg1 = fmaxf(vk.x, 1e-4f), sg2 = fmaxf(vk.y, 1e-4f);
                             const float gm = __fdiv_rn(sg1, fmaxf(sg1 + sg2, 1e-7f));
                             wq = f2(gm, 1.f - gm);
                         }
-                        if (EXT) {
-                            ab[j] = f2(wq.x * a.x + wq.y * a.y, wq.x * dvar.x + wq.y * dvar.y);
-                            cc[j] = mul2(dcov, wq);
-                        } else {
-                            ab[j] = f2(a.x + a.y, dvar.x + dvar.y);
-                            cc[j] = dcov;
-                        }
-                        if (ZMODE && q >= i0 && q < iend && pc >= j0 && pc < jend) {
-                            z_ss = add2(z_ss, S);
-                            z_cs = add2(z_cs, mul2(A2, rB2));
-                            z_sg = add2(z_sg, max2(vk, 1e-4f));
-                        }
+                        ab[j] = vj ? f2(wq.x * a.x + wq.y * a.y, wq.x * nb.x + wq.y * nb.y) : f2(0.f, 0.f);
+                        cc[j] = vj ? mul2(ch, wq) : f2(0.f, 0.f);
+                    } else {
+                        ab[j] = vj ? f2(a.x + a.y, nb.x + nb.y) : f2(0.f, 0.f);
+                        cc[j] = vj ? ch : f2(0.f, 0.f);
+                    }
+                    if (ZMODE) {
+                        const float2 zf = bcast(((zm >> j) & 1u) ? 1.f : 0.f);
+                        z_ss = fma2(zf, S, z_ss);
+                        z_cs = fma2(zf, Cs, z_cs);
+                        z_sg = fma2(zf, max2(vk, 1e-4f), z_sg);
                     }
                 }
             } else {
@@ -359,8 +414,8 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                     const float x1s = u1[j] - sh.c.x;
                     const float x2s = u2[j] - sh.c.y;
                     const float ys = uy[j] - sh.cy;
-                    const float dS = acc[j][0].x + 2.f * ys * acc[j][0].y + x1s * acc[j][1].x + x2s * acc[j][1].y;
-                    outv[j] = fmaf(k_ssim, dS, gb[j]);
+                    const float dS = fmaf(x2s, acc[j][1].y, fmaf(x1s, acc[j][1].x, fmaf(-ys, acc[j][0].y, acc[j][0].x)));   // dS / 2
+                    outv[j] = fmaf(k_ssim2, dS, gb[j]);
                 }
                 float* dst = p.dF + img_off + (size_t)i * p.W + j0 + hg * 8;
                 if (EXT && p.accum) {

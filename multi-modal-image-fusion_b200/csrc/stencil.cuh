@@ -107,6 +107,7 @@ struct Shift {
     float2 k0;       // eps c^2 s
     float k1y, k0y;
     float2 ec;       // eps c            (multiplies mu_y')
+    float2 nec;      // -eps c
     float ecy;       // eps cy           (multiplies mu_k')
     float2 eccs;     // eps c cy s
     float rho;       // window-sum mismatch of the separable taps (Taps::wrho)
@@ -123,6 +124,7 @@ __device__ __forceinline__ Shift make_shift(float c1, float c2, float cy, float 
     h.k1y = 2.f * eps * cy;
     h.k0y = eps * cy * cy * s;
     h.ec = f2(eps * c1, eps * c2);
+    h.nec = f2(-eps * c1, -eps * c2);
     h.ecy = eps * cy;
     h.eccs = f2(eps * c1 * cy * s, eps * c2 * cy * s);
     return h;
@@ -145,16 +147,18 @@ struct Stats {    // reference-equivalent statistics
 };
 __device__ __forceinline__ Stats stats_from(const Moments& m, const Shift& h) {
     Stats s;
+    const float2 nrho = bcast(-h.rho), neg1 = bcast(-1.f);
     s.mu = add2(m.mk, h.sc);
     s.muy = m.my + h.scy;
-    // vk = ekk - mk*mk - k1*mk - k0  + rho (ekk - 2 mk^2)   [rho: rescale the separable window sum]
-    float2 t = fma2(m.mk, add2(m.mk, h.k1), h.k0);        // mk*(mk+k1) + k0
-    const float2 r2 = bcast(h.rho);
-    s.vk = fma2(r2, fma2(muls(-2.f, m.mk), m.mk, m.ekk), f2(m.ekk.x - t.x, m.ekk.y - t.y));
-    s.vy = fmaf(h.rho, fmaf(-2.f * m.my, m.my, m.eyy), m.eyy - fmaf(m.my, m.my + h.k1y, h.k0y));
-    // cov = eky - mk*my - (ec*my + ecy*mk + eccs) + rho (eky - 2 mk my)
-    float2 u = fma2(m.mk, bcast(m.my + h.ecy), fma2(h.ec, bcast(m.my), h.eccs));
-    s.cov = fma2(r2, fma2(muls(-2.f * m.my, m.mk), bcast(1.f), m.eky), f2(m.eky.x - u.x, m.eky.y - u.y));
+    // vk = ekk - t - rho t, t = mk (mk + k1) + k0   [rho (ekk - 2 mk^2) = rho (ekk - t) - rho t; the first part is < 0.1 ulp
+    // of ekk - t and dropped, the second is what decides the sign of a flat region's variance]
+    const float2 t = fma2(m.mk, add2(m.mk, h.k1), h.k0);
+    s.vk = fma2(nrho, t, fma2(t, neg1, m.ekk));
+    const float ty = fmaf(m.my, m.my + h.k1y, h.k0y);
+    s.vy = fmaf(-h.rho, ty, m.eyy - ty);
+    // cov = eky - u - rho u, u = mk (my + ecy) + ec my + eccs
+    const float2 u = fma2(m.mk, bcast(m.my + h.ecy), fma2(h.ec, bcast(m.my), h.eccs));
+    s.cov = fma2(nrho, u, fma2(u, neg1, m.eky));
     return s;
 }
 
