@@ -187,7 +187,11 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
         // fully unrolled — the sliding state is renamed instead of moved, borders cost nothing.
         const bool s_fast = FAST && !EXT && p.do_sobel && s_strip_int && (Rb >= max(2, i0)) && (Rb + 9 <= min(iend, p.H - 1));
         if (s_fast) {
+            // Three passes over the 8 rows so that the 8 independent row chains overlap (the phase is
+            // latency-bound, not issue-bound): 1. loads, Sobel, sign factors; 2. neighbour exchange;
+            // 3. vertical combination and store.
             const int bb = (b & 3) * kRB + 2;
+            float tx[kRB], ty[kRB], pg[kRB];
 #pragma unroll
             for (int step = 0; step < kRB; ++step) {
                 const int lro = ((bb + step) & (SmemB::kRows - 1)) * kRPB;      // ring row of input row Rb + 2 + step
@@ -207,19 +211,29 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                 const float S1 = fabsf(gx.x) + fabsf(gy.x), S2 = fabsf(gx.y) + fabsf(gy.y), Sy = fabsf(gxy) + fabsf(gyy);
                 const float D = Sy - fmaxf(S1, S2);
                 const float r = mulsign(k_grad, D);
-                const float tx = mulsign(r, gxy), ty = mulsign(r, gyy);
-                if (ZMODE) z_grad = fmaf(s_ownf, fabsf(D), z_grad);
-                const float txl = __shfl_up_sync(0xffffffffu, tx, 1), txr = __shfl_down_sync(0xffffffffu, tx, 1);
-                const float tyl = __shfl_up_sync(0xffffffffu, ty, 1), tyr = __shfl_down_sync(0xffffffffu, ty, 1);
-                const float hx = txl - txr;
-                const float vy = fmaf(2.f, ty, tyl + tyr);
-                const float dp = s_ucAy - fmaxf(s_ucA.x, s_ucA.y);
-                const float G = (s_hxA + s_vyA) + fmaf(2.f, s_hxB, hx - vy) + mulsign(k_pix, dp);
-                s_gdst[step * (kTMC + 4)] = G;                             // lanes that own no column write a pad column
-                if (ZMODE) z_pix = fmaf(s_ownf, fabsf(dp), z_pix);
+                tx[step] = mulsign(r, gxy);
+                ty[step] = mulsign(r, gyy);
+                const float dp = s_ucAy - fmaxf(s_ucA.x, s_ucA.y);         // pixel term of row Rb + step
+                pg[step] = mulsign(k_pix, dp);
+                if (ZMODE) {
+                    z_grad = fmaf(s_ownf, fabsf(D), z_grad);
+                    z_pix = fmaf(s_ownf, fabsf(dp), z_pix);
+                }
                 s_dA = s_dB; s_dB = d; s_sA = s_sB; s_sB = sv; s_dAy = s_dBy; s_dBy = dy; s_sAy = s_sBy; s_sBy = sy;
-                s_hxA = s_hxB; s_hxB = hx; s_vyA = s_vyB; s_vyB = vy;
                 s_ucA = s_ucB; s_ucB = uc; s_ucAy = s_ucBy; s_ucBy = ucy;
+            }
+#pragma unroll
+            for (int step = 0; step < kRB; ++step) {
+                const float txl = __shfl_up_sync(0xffffffffu, tx[step], 1), txr = __shfl_down_sync(0xffffffffu, tx[step], 1);
+                const float tyl = __shfl_up_sync(0xffffffffu, ty[step], 1), tyr = __shfl_down_sync(0xffffffffu, ty[step], 1);
+                tx[step] = txl - txr;                                      // hx of row Rb + 1 + step
+                ty[step] = fmaf(2.f, ty[step], tyl + tyr);                 // vy
+            }
+#pragma unroll
+            for (int step = 0; step < kRB; ++step) {
+                const float hx = tx[step], vy = ty[step];
+                s_gdst[step * (kTMC + 4)] = (s_hxA + s_vyA) + fmaf(2.f, s_hxB, hx - vy) + pg[step];   // lanes owning no column write a pad column
+                s_hxA = s_hxB; s_hxB = hx; s_vyA = s_vyB; s_vyB = vy;
             }
         } else if (!EXT && p.do_sobel) {
 #pragma unroll 2
