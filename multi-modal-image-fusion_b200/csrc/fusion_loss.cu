@@ -29,7 +29,7 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
     BwdGeom g;
     g.Hout = H - (win - 1); g.Wout = W - (win - 1);
     g.nstrip = ceil_div(W, bwd_tg(win));
-    g.seg_rows = fwd_seg_rows(H, B * g.nstrip);
+    g.seg_rows = pick_seg_rows(H, B * g.nstrip, 2 * 148, 2 * (win - 1) + 8);   // 2 CTAs / SM; halo + batch rounding + prologue
     g.nseg = ceil_div(H, g.seg_rows);
     return g;
 }
@@ -351,7 +351,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                         cc[j] = vj ? ch : f2(0.f, 0.f);
                     }
                     if (ZMODE) {
-                        const float2 zf = bcast(((zm >> j) & 1u) ? 1.f : 0.f);
+                        const float2 zf = bcast(((zm >> j) & 1u) ? 1.f : 0.f);      // (masked columns hold finite values: zero-filled data, C1, C2 > 0)
                         z_ss = fma2(zf, S, z_ss);
                         z_cs = fma2(zf, Cs, z_cs);
                         z_sg = fma2(zf, max2(vk, 1e-4f), z_sg);

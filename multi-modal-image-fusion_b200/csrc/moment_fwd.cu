@@ -1,15 +1,28 @@
 // Instantiations and host launcher of the forward strip-streaming kernel.
+#include <math.h>
 #include "moment_fwd.cuh"
 
 namespace mmif {
 
-int fwd_seg_rows(int rows, int other_ctas) {
-    // largest segment (fewest halo rows) that still gives >= 2 CTAs per SM
-    const int target = 2 * 148;
-    int s = 256;
-    while (s > 16 && (long long)other_ctas * ceil_div(rows, s) < target) s >>= 1;
-    return s;
+// Rows per segment (a multiple of 8) for `rows` rows split among CTAs that each pay `extra_rows` rows of
+// halo / prologue work, with `other_ctas` strips x samples and `slots` CTAs resident on the chip:
+// minimise  waves x (seg_rows + extra_rows)  where waves counts the quantised tail of the last wave.
+int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows) {
+    int best_seg = 8;
+    double best = 1e300;
+    const int max_nseg = ceil_div(rows, 8);
+    for (int nseg = 1; nseg <= max_nseg; ++nseg) {
+        const int seg = ceil_div(ceil_div(rows, nseg), 8) * 8;
+        if (ceil_div(rows, seg) != nseg) continue;
+        const double w = (double)other_ctas * nseg / slots;
+        const double waves = fmax(ceil(w), w + 0.5);
+        const double cost = waves * (seg + extra_rows);
+        if (cost < best) { best = cost; best_seg = seg; }
+        if (seg <= 16) break;
+    }
+    return best_seg;
 }
+int fwd_seg_rows(int rows, int other_ctas) { return pick_seg_rows(rows, other_ctas, 3 * 148, 14); }
 
 static int two_of(int win) { return ((kTWI - (win - 1)) / 4) * 4; }
 

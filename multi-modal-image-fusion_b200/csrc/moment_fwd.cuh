@@ -265,6 +265,9 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
     const int chi = (strip == p.nstrip - 1) ? p.W : j0 + TWO + HALO / 2;
     constexpr float kVifEps = 1e-10f, kVifNoise = 325.125f;            // metric.py:407-408
 
+    unsigned cmask = 0u;                         // bit j: window column hg*8 + j exists
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cmask |= (hg * 8 + j < cols_out) ? (1u << j) : 0u;
     const bool fast_terms = p.pixel_combine == MMIF_COMBINE_MAX && p.grad_combine == MMIF_COMBINE_MAX &&
                             p.pixel_norm == MMIF_NORM_L1 && p.grad_norm == MMIF_NORM_L1 && p.denorm == nullptr;
     for (int b = 0; b < nb; ++b) {
@@ -283,62 +286,59 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
         if (ho < rows_b && hg * 8 < cols_out) {
             float2 acc[8][4];
             hpass<WIN, 4, false>(sm.vbuf + ho * kVPitch + hg * 8, kVCols, p.taps, acc);
+            // Branch-free over the 8 columns (their chains interleave); columns past the last window are
+            // computed on zero-filled data and dropped by a select.
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (hg * 8 + j < cols_out) {
-                    const Stats st = stats_from(moments_of(acc[j]), sh);
-                    const float2 vk = max2(st.vk, 0.f);
-                    const float vy = fmaxf(st.vy, 0.f);
-                    if (EPI == EPI_MSW) {               // gamma-weighted SSIM of the two pairs (loss.py:230-235)
-                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
-                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
-                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
-                        const float2 B2 = add2(vk, bcast(vy + p.C2));
-                        const float2 S = fdiv_nr2(mul2(A1, A2), mul2(B1, B2));
-                        const float sg1 = fmaxf(vk.x, 1e-4f), sg2 = fmaxf(vk.y, 1e-4f);
-                        const float gm = __fdiv_rn(sg1, fmaxf(sg1 + sg2, 1e-7f));
-                        s0 = add2(s0, f2(gm * S.x + (1.f - gm) * S.y, 0.f));
-                    } else if (EPI == EPI_MAPS) {       // size_average=False: the maps themselves (loss.py:99-108)
-                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
-                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
-                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
-                        const float2 B2 = add2(vk, bcast(vy + p.C2));
-                        const float2 S = fdiv_nr2(mul2(A1, A2), mul2(B1, B2)), CS = fdiv_nr2(A2, B2), SG = max2(vk, 1e-4f);
-                        const size_t o = ((size_t)n * p.Hout + (i0 + b * kRB + ho)) * p.Wout + (j0 + hg * 8 + j);
-                        if (p.maps[0]) p.maps[0][o] = S.x;
-                        if (p.maps[1]) p.maps[1][o] = CS.x;
-                        if (p.maps[2]) p.maps[2][o] = SG.x;
-                        if (p.maps[3]) p.maps[3][o] = S.y;
-                        if (p.maps[4]) p.maps[4][o] = CS.y;
-                        if (p.maps[5]) p.maps[5][o] = SG.y;
-                    } else if (EPI == EPI_SSIM) {
-                        const float2 A1 = fma2(muls(2.f, st.mu), bcast(st.muy), bcast(p.C1));
-                        const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
-                        const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
-                        const float2 B2 = add2(vk, bcast(vy + p.C2));
-                        s0 = add2(s0, fdiv_nr2(mul2(A1, A2), mul2(B1, B2)));
-                        s1 = add2(s1, fdiv_nr2(A2, B2));
-                        s2 = add2(s2, max2(vk, 1e-4f));
-                    } else {
-                        double fn[2], fd[2];
-                        float gg[2];
-                        const float v1[2] = {vk.x, vk.y}, c12[2] = {st.cov.x, st.cov.y};
+                const bool vj = (cmask >> j) & 1u;
+                const Stats st = stats_from(moments_of(acc[j]), sh);
+                const float2 vk = max2(st.vk, 0.f);
+                const float vy = fmaxf(st.vy, 0.f);
+                if (EPI == EPI_VIF) {
+                    double fn[2], fd[2];
+                    float gg[2];
+                    const float v1[2] = {vk.x, vk.y}, c12[2] = {st.cov.x, st.cov.y};
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            float sig1 = v1[k];
-                            float g = fdiv_nr(c12[k], sig1 + kVifEps);
-                            float sv = vy - g * c12[k];
-                            if (sig1 < kVifEps) { g = 0.f; sv = vy; sig1 = 0.f; }
-                            if (vy < kVifEps) { g = 0.f; sv = 0.f; }
-                            if (g < 0.f) { sv = vy; g = 0.f; }
-                            if (sv < kVifEps) sv = kVifEps;
-                            fn[k] = 1.0 + (double)fdiv_nr(g * g * sig1, sv + kVifNoise);
-                            fd[k] = 1.0 + (double)(sig1 * (1.0f / kVifNoise));
-                            gg[k] = g;
+                    for (int k = 0; k < 2; ++k) {
+                        float sig1 = v1[k];
+                        float g = fdiv_nr(c12[k], sig1 + kVifEps);
+                        float sv = vy - g * c12[k];
+                        if (sig1 < kVifEps) { g = 0.f; sv = vy; sig1 = 0.f; }
+                        if (vy < kVifEps) { g = 0.f; sv = 0.f; }
+                        if (g < 0.f) { sv = vy; g = 0.f; }
+                        if (sv < kVifEps) sv = kVifEps;
+                        fn[k] = 1.0 + (double)fdiv_nr(g * g * sig1, sv + kVifNoise);
+                        fd[k] = 1.0 + (double)(sig1 * (1.0f / kVifNoise));
+                        gg[k] = g;
+                    }
+                    const bool pick1 = gg[0] < gg[1];
+                    lp[0].mul(vj ? fn[0] : 1.0); lp[1].mul(vj ? fd[0] : 1.0); lp[2].mul(vj ? fn[1] : 1.0); lp[3].mul(vj ? fd[1] : 1.0);
+                    lp[4].mul(vj ? (pick1 ? fn[0] : fn[1]) : 1.0); lp[5].mul(vj ? (pick1 ? fd[0] : fd[1]) : 1.0);
+                } else {
+                    const float2 A1 = fma2(st.mu, bcast(2.f * st.muy), bcast(p.C1));
+                    const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
+                    const float2 A2 = fma2(bcast(2.f), st.cov, bcast(p.C2));
+                    const float2 B2 = add2(vk, bcast(vy + p.C2));
+                    const float2 CS = mul2(A2, rcp2(B2));
+                    const float2 S = mul2(mul2(A1, rcp2(B1)), CS);
+                    const float2 SG = max2(vk, 1e-4f);
+                    if (EPI == EPI_MSW) {               // gamma-weighted SSIM of the two pairs (loss.py:230-235)
+                        const float gm = __fdiv_rn(SG.x, fmaxf(SG.x + SG.y, 1e-7f));
+                        s0.x += vj ? (gm * S.x + (1.f - gm) * S.y) : 0.f;
+                    } else if (EPI == EPI_MAPS) {       // size_average=False: the maps themselves (loss.py:99-108)
+                        if (vj) {
+                            const size_t o = ((size_t)n * p.Hout + (i0 + b * kRB + ho)) * p.Wout + (j0 + hg * 8 + j);
+                            if (p.maps[0]) p.maps[0][o] = S.x;
+                            if (p.maps[1]) p.maps[1][o] = CS.x;
+                            if (p.maps[2]) p.maps[2][o] = SG.x;
+                            if (p.maps[3]) p.maps[3][o] = S.y;
+                            if (p.maps[4]) p.maps[4][o] = CS.y;
+                            if (p.maps[5]) p.maps[5][o] = SG.y;
                         }
-                        const bool pick1 = gg[0] < gg[1];
-                        lp[0].mul(fn[0]); lp[1].mul(fd[0]); lp[2].mul(fn[1]); lp[3].mul(fd[1]);
-                        lp[4].mul(pick1 ? fn[0] : fn[1]); lp[5].mul(pick1 ? fd[0] : fd[1]);
+                    } else {
+                        s0 = add2(s0, f2(vj ? S.x : 0.f, vj ? S.y : 0.f));
+                        s1 = add2(s1, f2(vj ? CS.x : 0.f, vj ? CS.y : 0.f));
+                        s2 = add2(s2, f2(vj ? SG.x : 0.f, vj ? SG.y : 0.f));
                     }
                 }
             }
@@ -373,6 +373,7 @@ struct FwdLaunch {
     float* maps[6];          // EPI_MAPS outputs
     unsigned char* denorm;   // do_sobel: uint8 image of y (or NULL)
 };
+int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows);
 int fwd_seg_rows(int rows, int other_ctas);
 size_t fwd_ws_bytes(int win, int B, int H, int W);       // counters + partials (sums live elsewhere)
 // ws: zero-initialised workspace of fwd_ws_bytes; sums: B x sums_stride doubles (device).
