@@ -101,7 +101,9 @@ int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B
  * gout3: 3 floats in DEVICE memory (upstream gradients of the three loss values).
  * dF_unit: NULL, or the buffer a want_grad forward (same inputs, same cfg) filled.  When it is given
  * and the three upstream gradients are equal (total = l1 + l2 + l3, train.py:69) the kernel only
- * rescales it (8 B/pixel); otherwise it recomputes.  The decision is taken on the device. */
+ * rescales it (8 B/pixel); otherwise it recomputes.  The decision is taken on the device.
+ * dF may alias dF_unit: the rescale then happens in place and costs nothing when the common upstream
+ * gradient is exactly 1 (total.backward()); the buffer no longer holds the unit gradient afterwards. */
 int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
                          const MmifLossCfg* cfg, const float* gout3, const float* dF_unit, float* dF,
                          void* ws, size_t ws_bytes, void* stream);

@@ -82,9 +82,11 @@ class _FusedObjective(torch.autograd.Function):
         dev = y.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g = torch.stack([zero if t is None else t.to(torch.float32).reshape(()) for t in (g_ssim, g_pix, g_grad)])
-        dF = torch.empty_like(y)
         cfg = _cfg(*ctx.cfg_key)
-        unit = ctx.dF_unit
+        # The single-pass buffer is consumed by the first backward: it is rescaled IN PLACE (nothing to do at all for
+        # the unit upstream of total.backward()) and handed to autograd; a second backward (retain_graph) recomputes.
+        unit, ctx.dF_unit = ctx.dF_unit, None
+        dF = unit if unit is not None else torch.empty_like(y)
         ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
         with torch.cuda.device(dev):
             L.check(lib.mmif_fusion_loss_bwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),

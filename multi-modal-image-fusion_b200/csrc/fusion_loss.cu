@@ -462,6 +462,7 @@ __global__ void __launch_bounds__(256)
 rescale_unit_kernel(const float* __restrict__ gout, const float* __restrict__ unit, float* __restrict__ dF, size_t n, int vec) {
     const float g0 = __ldg(gout + 0), g1 = __ldg(gout + 1), g2 = __ldg(gout + 2);
     if (!(g0 == g1 && g1 == g2)) return;
+    if (unit == dF && g0 == 1.f) return;          // in place with unit upstream (total.backward()): the buffer already is dL/dIf
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
@@ -645,7 +646,6 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     if (rc) return rc;
     if (!gout3 || !dF) { set_error("null gout3/dF"); return MMIF_E_NULL; }
     if ((((uintptr_t)dF) | ((uintptr_t)dF_unit)) & 3) { set_error("dF / dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
-    if (dF_unit == dF) { set_error("dF must not alias dF_unit"); return MMIF_E_MODE; }
     return launch_bwd(i1, i2, f, B, H, W, cfg, gout3, dF_unit, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 
