@@ -76,14 +76,27 @@ pixel_metrics_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) dA[k] = dB[k] = sA[k] = sB[k] = pc[k] = 0.f;
     float pfr = 0.f;
-    for (int r = r0 - 1; r <= r1; ++r) {
+    // the loads of row r+1 are issued before row r is consumed (one row of prefetch hides the global latency)
+    float nuc[3], nxl[3], nxr[3];
+    auto fetch = [&](int r) {
         const int rr = (r < 0) ? -r : ((r >= H) ? 2 * H - 2 - r : r);
-        float gx[3], gy[3], uc[3], upf = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float* row = img[k] + (size_t)rr * W + c;
-            uc[k] = __ldg(row);
-            const float xl = ldL ? __ldg(row - 1) : 0.f, xr = ldR ? __ldg(row + 1) : 0.f;
+            nuc[k] = __ldg(row);
+            nxl[k] = ldL ? __ldg(row - 1) : 0.f;
+            nxr[k] = ldR ? __ldg(row + 1) : 0.f;
+        }
+    };
+    fetch(r0 - 1);
+    for (int r = r0 - 1; r <= r1; ++r) {
+        float gx[3], gy[3], uc[3], xls[3], xrs[3], upf = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { uc[k] = nuc[k]; xls[k] = nxl[k]; xrs[k] = nxr[k]; }
+        if (r < r1) fetch(r + 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float xl = xls[k], xr = xrs[k];
             float um = __shfl_up_sync(0xffffffffu, uc[k], 1), up = __shfl_down_sync(0xffffffffu, uc[k], 1);
             if (lane == 0) um = xl;
             if (lane == 31) up = xr;
