@@ -242,8 +242,16 @@ def main():
                 'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
                 'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
                 'ms_per_launch': ms_z,
-                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/r1d_zkernel.txt: FMA pipe 61% active, '
-                        'DRAM 8%): 1056 packed FMAs per 8 output pixels put the pipe roof of this kernel at ~64 Gpix/s'}
+                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/r1e_zkernel.txt: FMA pipe 65% active, '
+                        'DRAM 9.5%, traffic 16.8 B/px): 264 FMA/px of exact-fp32 separable blurs alone cap the kernel at 27% of the HBM roof; '
+                        'see roofline_fp32 for the roof that binds'}
+    # secondary roof, the one that binds: ALGORITHMIC fp32 FMAs (12 blurred maps x 2 passes x 11 taps = 264 FMA/px, the
+    # irreducible part; epilogue / Sobel / products excluded) against the measured packed-FMA issue rate of B200
+    # (tools/microbench/pipes.cu, profiles/pipes_r1.txt: 58.4 FFMA2/clk/SM = 116.8 FMA/clk/SM at 1965 MHz x 148 SMs)
+    fma_peak = 116.8 * 148 * 1.965e9 / 1e12
+    fma_ach = 264.0 * local_pix / (ms_z * 1e-3) / 1e12
+    roofline_fp32 = {'bound': 'fp32 FMA pipe', 'achieved': fma_ach, 'peak': fma_peak, 'unit': 'TFMA/s', 'frac': fma_ach / fma_peak,
+                     'algorithmic_fma_per_pixel': 264, 'peak_source': 'measured FFMA2 issue rate (profiles/pipes_r1.txt)'}
     two_kernel = {'value': total_mpix / (ms_step2 * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step2,
                   'fwd': {'kernel': 'moment_fwd_kernel<11,EPI_SSIM>', 'ms_per_launch': ms_fwd, 'achieved': gbs(ALG_BYTES_FWD, ms_fwd),
                           'frac': gbs(ALG_BYTES_FWD, ms_fwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_FWD},
@@ -260,7 +268,7 @@ def main():
                    'path': 'single-pass (loss + gradient in one launch; backward rescales that buffer in place, a no-op for unit upstream); two_kernel = fwd then recomputing bwd',
                    'l2': 'inputs larger than L2 (per-rank tensors %.0f MB each)' % (B * H * W * 4 / 1e6),
                    'collective': 'one 16-byte all-reduce of the loss scalars per step' if world > 1 else 'none'},
-        'roofline': roofline, 'rescale_ms': ms_rescale, 'two_kernel': two_kernel, 'clocks': clocks,
+        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'backward_ms': ms_rescale, 'two_kernel': two_kernel, 'clocks': clocks,
         'gpu_launches': 3 * args.steps,
     }
 
