@@ -157,7 +157,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     const bool s_strip_int = (j0 >= 3) && (j0 + kTG <= p.W - 3);
     const float* s_p0 = &sm.ring[0][0][min(max(s_c - jw0, 1), kRPB - 2)];
     const float s_ownf = s_own ? 1.f : 0.f;
-    float* s_gdst = &sb.gbuf[0][s_own ? s_ci : kTMC];
+    float* s_gdst = &sb.gbuf[0][s_own ? s_ci : 0];
     float2 s_dA = f2(0.f, 0.f), s_dB = s_dA, s_sA = s_dA, s_sB = s_dA, s_ucA = s_dA, s_ucB = s_dA;
     float s_dAy = 0.f, s_dBy = 0.f, s_sAy = 0.f, s_sBy = 0.f, s_ucAy = 0.f, s_ucBy = 0.f;
     float s_hxA = 0.f, s_hxB = 0.f, s_vyA = 0.f, s_vyB = 0.f;
@@ -232,7 +232,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
 #pragma unroll
             for (int step = 0; step < kRB; ++step) {
                 const float hx = tx[step], vy = ty[step];
-                s_gdst[step * (kTMC + 4)] = (s_hxA + s_vyA) + fmaf(2.f, s_hxB, hx - vy) + pg[step];   // lanes owning no column write a pad column
+                if (s_own) s_gdst[step * (kTMC + 4)] = (s_hxA + s_vyA) + fmaf(2.f, s_hxB, hx - vy) + pg[step];
                 s_hxA = s_hxB; s_hxB = hx; s_vyA = s_vyB; s_vyB = vy;
             }
         } else if (!EXT && p.do_sobel) {
