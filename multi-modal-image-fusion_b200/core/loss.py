@@ -202,6 +202,51 @@ class _WeightedSSIM(torch.autograd.Function):
         return None, None, dF.view(ctx.in_shape), None
 
 
+class _SSIMDict(torch.autograd.Function):
+    """SSIM.forward (loss.py:163-185 -> calc_ssim, loss.py:52-110) with size_average=True, differentiable:
+    (img1, img2) -> per-sample (ssim, cs, sigma).  SSIM and CS are symmetric in their arguments, so the gradient
+    w.r.t. either image is the 'fused image' gradient of the SSIM-only backward kernel with the other image as the
+    source and the upstream per-sample gradients as pair weights; sigma = clamp(var(img1), 1e-4) does not depend on img2."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, data_range):
+        x, B, H, W = L.as_f32_3d(img1.detach(), 'img1')
+        y, _, _, _ = L.as_f32_3d(img2.detach(), 'img2')
+        if y.shape != x.shape:
+            raise L.MmifError(f'shape mismatch: {tuple(img1.shape)} {tuple(img2.shape)}')
+        L.ensure_device(x.device)
+        x, y = x.view(B, H, W), y.view(B, H, W)
+        ps = _fwd_per_sample(x, x, y, data_range).to(torch.float32)
+        ctx.save_for_backward(x, y)
+        ctx.data_range, ctx.shape1, ctx.shape2 = data_range, img1.shape, img2.shape
+        ctx.set_materialize_grads(False)
+        return ps[:, 0].clone(), ps[:, 1].clone(), ps[:, 2].clone()
+
+    @staticmethod
+    def backward(ctx, g_ssim, g_cs, g_sigma):
+        x, y = ctx.saved_tensors
+        one = torch.ones(1, dtype=torch.float32, device=x.device)
+
+        def wrt(src, tgt):          # d/d tgt of sum_n g_ssim[n] ssim_n + g_cs[n] cs_n
+            out = None
+            for g, cs_only in ((g_ssim, 0), (g_cs, 1)):
+                if g is None:
+                    continue
+                pw = torch.stack([g.to(torch.float32).reshape(-1), torch.zeros_like(g, dtype=torch.float32).reshape(-1)], dim=1)
+                d = _ssim_bwd_ex(src, src, tgt, ctx.data_range, one, pw, cs_only, 1.0)
+                out = d if out is None else out + d
+            return out if out is not None else torch.zeros_like(tgt)
+
+        g1 = g2 = None
+        if ctx.needs_input_grad[1]:
+            g2 = wrt(x, y).view(ctx.shape2)
+        if ctx.needs_input_grad[0]:
+            if g_sigma is not None:
+                raise NotImplementedError("gradient of SSIM.forward()['sigma'] w.r.t. img1 is not built")
+            g1 = wrt(y, x).view(ctx.shape1)
+        return g1, g2, None
+
+
 def _pad_raw(x, pad):
     """(B,H,W) -> reflect-padded (B,H+2p,W+2p); F.pad(.., 'reflect') of use_padding=True (loss.py:45-47)."""
     lib = L.load()
@@ -427,10 +472,16 @@ def _ssim_dict(img1, img2, data_range, use_padding, size_average, win_size=11):
         raise NotImplementedError('only the 11-tap window of the training objective is built')
     if data_range is None:
         data_range = _auto_range(img1)
-    if img2.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError('SSIM.forward is forward-only here; use SSIMLoss for the differentiable objective')
+    needs_grad = torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad)
     if not size_average:
+        if needs_grad:
+            raise NotImplementedError('gradients through the SSIM maps (size_average=False) are not built')
         return ssim_maps(img1, img2, data_range)
+    if needs_grad:
+        for t, nm in ((img1, 'img1'), (img2, 'img2')):
+            L.require_cuda(t, nm)
+        ss, cs, sg = _SSIMDict.apply(img1, img2, data_range)
+        return {'ssim': ss, 'cs': cs, 'sigma': sg}
     _, _, _, ps = _fused(img1, img1, img2, data_range=data_range)
     return {'ssim': ps[:, 0], 'cs': ps[:, 1], 'sigma': ps[:, 2]}
 

@@ -302,3 +302,36 @@ def test_norm_loss_forward_backward(mode):
     g64, = torch.autograd.grad(l64, xd)
     assert abs(l.item() - l64.item()) <= 1e-6 * abs(l64.item())
     np.testing.assert_allclose(gx.cpu().numpy(), g64.numpy(), rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize('use_padding', [False, True])
+def test_ssim_module_dict_is_differentiable(use_padding):
+    """SSIM.forward (loss.py:163-185): gradients of the per-sample 'ssim' and 'cs' entries w.r.t. BOTH images,
+    against the fp64 oracle's autograd (max-norm gate of the loss gradients)."""
+    ML = _mods()
+    a, _, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    w1 = torch.tensor([0.7, -1.3, 2.0])
+    w2 = torch.tensor([1.5, 0.25, -0.5])
+
+    def obj(d, dt):
+        return (w1.to(d['ssim'].device, dt) * d['ssim']).sum() + (w2.to(d['cs'].device, dt) * d['cs']).sum() + 0.0 * d['sigma'].sum()
+
+    A, F_ = a.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+    d = ML.SSIM(11, 1.0, use_padding).cuda()(A, F_)
+    val = (w1.cuda() * d['ssim']).sum() + (w2.cuda() * d['cs']).sum()
+    gA, gF = torch.autograd.grad(val, (A, F_))
+    a64, f64 = a.double().requires_grad_(True), f.double().requires_grad_(True)
+    ref = obj(OL.ssim(a64, f64, 11, None, 1.0, use_padding), torch.float64)
+    rA, rF = torch.autograd.grad(ref, (a64, f64))
+    a32, f32 = a.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    r32 = obj(OL.ssim(a32, f32, 11, None, 1.0, use_padding), torch.float32)
+    qA, qF = torch.autograd.grad(r32, (a32, f32))
+    gates.assert_scalar('dict objective', val.item(), r32.item(), ref.item())
+    for nm, got, r64, q32 in (('d/d img1', gA, rA, qA), ('d/d img2', gF, rF, qF)):
+        frac, mx, where = gates.grad_report(got.cpu().numpy(), r64.numpy())
+        ref_err = np.abs(q32.numpy() - r64.numpy()).max() / np.abs(r64.numpy()).max()
+        assert mx <= max(1e-5, ref_err), f'{nm}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+    # the clamped variance of img1 is not differentiable here w.r.t. img1: loud, not silent
+    d = ML.SSIM(11, 1.0).cuda()(A, F_)
+    with pytest.raises(NotImplementedError):
+        d['sigma'].sum().backward()
