@@ -12,17 +12,20 @@
 namespace mmif {
 
 constexpr int WIN11 = 11;
-// Backward tile geometry for a WIN-tap window: the tile origin is j0 - OFF (TMA: a multiple of 4
-// columns, >= HALO); TG gradient columns per strip (TG + OFF + HALO <= 128, multiple of 4); WC window
-// columns carry valid moments.  WIN = 11: OFF 12, TG 104, WC 118.
+// Backward tile geometry for a WIN-tap window: the ring origin is j0 - OFF (a multiple of 4 columns,
+// >= HALO, so that the float4 reads of the combine step stay aligned); the 128 V-pass threads take ring
+// columns VOFF .. VOFF+127 (the ring rows are 132 wide), i.e. image columns from j0 - HALO, so the WC =
+// 128 - HALO window columns start exactly HALO left of the gradient strip and TG = 128 - 2 HALO gradient
+// columns (rounded down to a multiple of 4) come out of every strip.  WIN = 11: OFF 12, VOFF 2, TG 108, WC 118.
 template <int WIN>
 struct BG {
     static constexpr int HALO = WIN - 1;
     static constexpr int OFF = (HALO + 3) / 4 * 4;
-    static constexpr int TG = (kTWI - OFF - HALO) / 4 * 4;
+    static constexpr int VOFF = OFF - HALO;
+    static constexpr int TG = (kTWI - 2 * HALO) / 4 * 4;
     static constexpr int WC = kTWI - HALO;
 };
-static int bwd_tg(int win) { const int halo = win - 1, off = (halo + 3) / 4 * 4; return (kTWI - off - halo) / 4 * 4; }
+static int bwd_tg(int win) { const int halo = win - 1; return (kTWI - 2 * halo) / 4 * 4; }
 
 struct BwdGeom { int Hout, Wout, seg_rows, nseg, nstrip; };
 static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
@@ -59,7 +62,7 @@ struct BwdParams {
 };
 
 constexpr int kCPitch = 2 * kTWI + 2;   // float2 units per coefficient row (2 pair-maps x 128 + 16 B pad)
-constexpr int kTMC = 120;               // gbuf columns (>= the widest gradient strip)
+constexpr int kTMC = 128;               // gbuf columns (>= the widest gradient strip: 124 for WIN = 3)
 
 constexpr int kRPB = kTWI + 4;           // backward ring row pitch (132 floats = 16 mod 128 B)
 using SmemB = SmemT<4, kRPB>;
@@ -72,7 +75,7 @@ __device__ __forceinline__ float mulsign(float r, float g) {
 struct SmemBwd {
     SmemB s;                             // ring + vbuf (vbuf also hosts the B1->B2 buffer)
     alignas(16) float2 cbuf[kRB * kCPitch];          // coefficient rows of the current batch: (a,b) and (c1,c2)
-    alignas(16) float gbuf[kRB][kTMC + 4];   // pixel + Sobel gradient of the batch rows (row pitch 496 B = 112 mod 128)
+    alignas(16) float gbuf[kRB][kTMC + 4];   // pixel + Sobel gradient of the batch rows (row pitch 528 B = 16 mod 128)
 };
 
 // FAST : mode='max' + 'l1' for both terms (train.py:67-68,307-308), no run-time mode switches.
@@ -85,13 +88,13 @@ template <int WIN, bool FAST, bool ZMODE, bool EXT>
 __global__ void __launch_bounds__(kNT, 2)
 fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
-    constexpr int HALO = BG<WIN>::HALO, kOFF = BG<WIN>::OFF, kTG = BG<WIN>::TG, kWC = BG<WIN>::WC;
+    constexpr int HALO = BG<WIN>::HALO, kOFF = BG<WIN>::OFF, kVOFF = BG<WIN>::VOFF, kTG = BG<WIN>::TG, kWC = BG<WIN>::WC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemBwd& sb = *reinterpret_cast<SmemBwd*>(smem_raw);
     SmemB& sm = sb.s;
     const int strip = blockIdx.x, seg = blockIdx.y, n = blockIdx.z;
     const int j0 = strip * kTG, i0 = seg * p.seg_rows;
-    const int jw0 = j0 - kOFF;             // first window / input column of the tile (multiple of 4: TMA)
+    const int jw0 = j0 - kOFF;             // first input column of the ring (multiple of 4); windows start at jw0 + kVOFF
     const int R0 = i0 - HALO;              // first window / input row of the segment
     const int iend = min(i0 + p.seg_rows, p.H);
     const int jend = min(j0 + kTG, p.W);
@@ -169,7 +172,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     unsigned a_vmask = 0u, a_zmask = 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int pw = hg * 8 + j, pc = jw0 + pw;
+        const int pw = hg * 8 + j, pc = jw0 + kVOFF + pw;
         const bool v = (pw < kWC) && (pc >= 0) && (pc < p.Wout);
         a_vmask |= v ? (1u << j) : 0u;
         a_zmask |= (v && pc >= j0 && pc < jend) ? (1u << j) : 0u;
@@ -293,7 +296,7 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
             }
         }
         // ---------------- A1: vertical moments of window rows [Rb, Rb+8) ------------------------
-        vpass_moments<WIN>(sm, p.taps, sh, (b & 3) * kRB);
+        vpass_moments<WIN>(sm, p.taps, sh, (b & 3) * kRB, kVOFF);
         __syncthreads();
         // ---------------- A2: horizontal moments -> derivative coefficients -> cbuf -------------
         {
@@ -404,8 +407,8 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
             const int i = Rb + ho;
             if (i >= i0 && i < iend && hg * 8 < kTG && j0 + hg * 8 < jend) {
                 float2 acc[8][2];
-                // gradient column g sums window columns [g + kOFF - HALO, g + kOFF] of the tile
-                hpass<WIN, 2, true>(tbuf + ho * kCPitch + hg * 8 + (kOFF - HALO), kTWI, p.taps, acc);
+                // gradient column g sums window columns [g, g + HALO] of the tile (window 0 = image column j0 - HALO)
+                hpass<WIN, 2, true>(tbuf + ho * kCPitch + hg * 8, kTWI, p.taps, acc);
                 const int lr = (b * kRB + ho) & (SmemB::kRows - 1);
                 float outv[8], u1[8], u2[8], uy[8], gb[8];
                 {   // 8 pixels of row lr: LDS.128, lanes 0-7 are 8 ring rows (pitch = 16 mod 128 B)
@@ -440,6 +443,8 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                 if (p.vec_store && j0 + hg * 8 + 8 <= jend) {
                     reinterpret_cast<float4*>(dst)[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
                     reinterpret_cast<float4*>(dst)[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);
+                } else if (p.vec_store && j0 + hg * 8 + 4 == jend) {      // half group at the strip end (TG = 4 mod 8) / image edge
+                    reinterpret_cast<float4*>(dst)[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)

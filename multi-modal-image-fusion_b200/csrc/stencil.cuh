@@ -163,18 +163,19 @@ __device__ __forceinline__ Stats stats_from(const Moments& m, const Shift& h) {
 }
 
 // ---- V-pass: vertical WIN-tap blur of the four packed moment maps --------------------------
-// `base` = ring-local index of the first input row of this batch (multiple of 8).
+// `base` = ring-local index of the first input row of this batch (multiple of 8); thread t blurs ring
+// column t + coff and writes vbuf column t.
 template <int WIN, class SM>
-__device__ __forceinline__ void vpass_moments(SM& sm, const Taps& tp, const Shift& h, int base) {
-    const int t = threadIdx.x;
+__device__ __forceinline__ void vpass_moments(SM& sm, const Taps& tp, const Shift& h, int base, int coff = 0) {
+    const int t = threadIdx.x, tr = t + coff;
     float2 acc[kRB][4];
     const float2 negc = f2(-h.c.x, -h.c.y);
 #pragma unroll
     for (int rr = 0; rr < kRB + WIN - 1; ++rr) {
         const int lr = SM::wrap(base + rr);
-        const float y = sm.ring[2][lr][t] - h.cy;
+        const float y = sm.ring[2][lr][tr] - h.cy;
         float2 P[4];
-        P[0] = add2(f2(sm.ring[0][lr][t], sm.ring[1][lr][t]), negc);
+        P[0] = add2(f2(sm.ring[0][lr][tr], sm.ring[1][lr][tr]), negc);
         P[1] = mul2(P[0], P[0]);
         P[2] = muls(y, P[0]);
         P[3] = f2(y, y * y);
