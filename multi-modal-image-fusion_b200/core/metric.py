@@ -429,6 +429,72 @@ def eval_metrics_batch_u8(img1, img2, imgf):
     return out.view(n, L.EVAL_METRICS)
 
 
+_copy_streams = {}
+
+
+def eval_metrics_batch_host(img1, img2, imgf, chunks=4):
+    """HOST images (float32 as eval.py:189-194 builds them, or uint8 as cv2 decodes them, eval.py:182-187; pinned memory
+    for real overlap) -> (N,16) float64 rows on the GPU, with the upload pipelined against the suite: the N pairs go in
+    ``chunks`` pieces through two device staging buffers, piece k+1 copies on a side stream while piece k computes.
+    Rows equal ``eval_metrics_batch`` up to the fp32 summation order of a different batch split (~2e-6 relative, the
+    histogram metrics exactly).  Asynchronous like the other entries: the caller's ``.cpu()`` / ``.item()`` syncs."""
+    lib = L.load()
+    ts = []
+    for t in (img1, img2, imgf):
+        if t.is_cuda:
+            raise L.MmifError('eval_metrics_batch_host takes host tensors (use eval_metrics_batch / _u8 for device tensors)')
+        if t.dtype not in (torch.uint8, torch.float32) or t.dtype != img1.dtype:
+            raise L.MmifError(f'uint8 or float32 expected (all three alike), got {t.dtype}')
+        if t.dim() == 4:
+            if t.shape[1] != 1:
+                raise L.MmifError(f'single-channel (N,1,H,W) expected, got {tuple(t.shape)}')
+            t = t[:, 0]
+        elif t.dim() == 2:
+            t = t.unsqueeze(0)
+        ts.append(t.contiguous())
+    n, h, w = ts[0].shape
+    if any(tuple(t.shape) != (n, h, w) for t in ts):
+        raise L.MmifError('shape mismatch between the three images')
+    is_u8 = ts[0].dtype == torch.uint8
+    dev = _default_device()
+    L.ensure_device(dev)
+    nchunk = max(1, min(int(chunks), n))
+    base, extra = divmod(n, nchunk)
+    sizes = [base + (1 if c < extra else 0) for c in range(nchunk)]
+    comp = torch.cuda.current_stream(dev)
+    copy = _copy_streams.get(dev.index)
+    if copy is None:
+        copy = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    out = torch.empty(n * L.EVAL_METRICS, dtype=torch.float64, device=dev)
+    stage = [[torch.empty((sizes[0], h, w), dtype=ts[0].dtype, device=dev) for _ in range(3)] for _ in range(min(2, nchunk))]
+    scratch = torch.empty(3 * sizes[0] * h * w, dtype=torch.float32, device=dev) if is_u8 else None
+    ready = [torch.cuda.Event() for _ in stage]
+    free = [torch.cuda.Event() for _ in stage]
+    copy.wait_stream(comp)              # the staging blocks may be recycled memory of earlier work on this stream
+    lo = 0
+    with torch.cuda.device(dev):
+        for c, nc in enumerate(sizes):
+            s = c & 1
+            with torch.cuda.stream(copy):
+                if c >= 2:
+                    copy.wait_event(free[s])
+                for k in range(3):
+                    stage[s][k][:nc].copy_(ts[k][lo:lo + nc], non_blocking=True)
+                ready[s].record(copy)
+            comp.wait_event(ready[s])
+            ws = _ws(dev, nc, h, w)
+            optr = out.data_ptr() + lo * L.EVAL_METRICS * 8
+            p = [t.data_ptr() for t in stage[s]]
+            if is_u8:
+                L.check(lib.mmif_eval_suite_u8(p[0], p[1], p[2], nc, h, w, optr, scratch.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               L.stream_ptr(dev)))
+            else:
+                L.check(lib.mmif_eval_suite(p[0], p[1], p[2], nc, h, w, optr, ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+            free[s].record(comp)
+            lo += nc
+    return out.view(n, L.EVAL_METRICS)
+
+
 def eval_metrics(img1, img2, imgf):
     """The dict eval.py:29-75 builds for one pair (python floats), through the fused suite entry."""
     _single(img1, 'eval_metrics')

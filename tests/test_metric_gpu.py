@@ -211,6 +211,29 @@ def test_uint8_ingest_equals_float_path():
         assert torch.equal(got, ref)
 
 
+def test_pipelined_host_ingest_equals_batched_entry():
+    """eval_metrics_batch_host: chunked upload overlapped with the suite; rows = the one-launch batched entry up to the
+    fp32 summation order of a different batch split (histogram metrics EN/MI/CE exactly)."""
+    MM = _mods()
+    g = torch.Generator().manual_seed(14)
+    a = torch.randint(0, 256, (9, 1, 140, 212), generator=g, dtype=torch.uint8)
+    b = torch.randint(0, 256, (9, 1, 140, 212), generator=g, dtype=torch.uint8)
+    f = ((a.int() + b.int()) // 2).to(torch.uint8)
+    ref = MM.eval_metrics_batch(a.float().cuda(), b.float().cuda(), f.float().cuda()).cpu().numpy()
+    for src in ((a.pin_memory(), b.pin_memory(), f.pin_memory()), (a, b, f),
+                (a.float().pin_memory(), b.float().pin_memory(), f.float().pin_memory())):
+        for chunks in (4, 1, 16):
+            got = MM.eval_metrics_batch_host(*src, chunks=chunks).cpu().numpy()
+            np.testing.assert_allclose(got, ref, rtol=5e-6, atol=2e-8)
+    names = list(OM.METRIC_NAMES)
+    got = MM.eval_metrics_batch_host(a.pin_memory(), b.pin_memory(), f.pin_memory()).cpu().numpy()
+    for nm in ('en', 'mi', 'ce'):
+        if nm in names:
+            assert np.array_equal(got[:, names.index(nm)], ref[:, names.index(nm)]), nm
+    with pytest.raises(Exception):
+        MM.eval_metrics_batch_host(a.cuda(), b.cuda(), f.cuda())
+
+
 def test_test_py_post_step_one_pass():
     """test.py:49-73: avg SSIM (data_range=1.0) and the denorm() image; the image must be bit-exact."""
     MM = _mods()
