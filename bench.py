@@ -242,8 +242,8 @@ def main():
                 'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
                 'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
                 'ms_per_launch': ms_z,
-                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/r1e_zkernel.txt: FMA pipe 65% active, '
-                        'DRAM 9.5%, traffic 16.8 B/px): 264 FMA/px of exact-fp32 separable blurs alone cap the kernel at 27% of the HBM roof; '
+                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/r1f_zkernel.txt: FMA pipe 66% active, '
+                        'DRAM 9.8%, traffic 17.0 B/px): 264 FMA/px of exact-fp32 separable blurs alone cap the kernel at 27% of the HBM roof; '
                         'see roofline_fp32 for the roof that binds'}
     # secondary roof, the one that binds: ALGORITHMIC fp32 FMAs (12 blurred maps x 2 passes x 11 taps = 264 FMA/px, the
     # irreducible part; epilogue / Sobel / products excluded) against the measured packed-FMA issue rate of B200
