@@ -29,6 +29,17 @@ bool make_tensor_map(CUtensorMap* map, const float* base, int N, int H, int W, i
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device: one bit per device ordinal, so a process that drives several
+// GPUs raises the dynamic shared-memory limit on each of them (a repeated set after a benign race is harmless).
+static inline bool first_use_on_device(unsigned long long* mask) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (d & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
+
 constexpr int kMaxWin = 17;
 struct Taps {          // Gaussian taps of one window, passed by value in kernel parameter space
     float w[kMaxWin];  // float32 taps exactly as the reference builds them (loss.py:24-30)

@@ -573,8 +573,8 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     p.use_tma = make_tensor_map(&m1, i1, B, H, W, kRPB, kRB) && make_tensor_map(&m2, i2, B, H, W, kRPB, kRB) &&
                 make_tensor_map(&my, f, B, H, W, kRPB, kRB);
     if (!p.use_tma) { memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2)); memset(&my, 0, sizeof(my)); }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0ull;
+    if (first_use_on_device(&attr_done)) {
         const int sz = (int)sizeof(SmemBwd);
         const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<11, true, false, false>, at, sz));
@@ -586,7 +586,6 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<7, false, false, true>, at, sz));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false, true>, at, sz));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false, true>, at, sz));
-        attr_done = true;
     }
     dim3 grid(g.nstrip, g.nseg, B);
     if (!zmode && dF_unit) {

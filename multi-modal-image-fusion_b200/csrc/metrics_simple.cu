@@ -398,10 +398,9 @@ int launch_hist(const float* a, const float* b, const float* f, int N, int H, in
     const long long P = (long long)H * W;
     int S = 1;
     if (2 * N < 32 && P >= 65536) { S = 148 / (2 * N); S = S < 1 ? 1 : (S > 16 ? 16 : S); }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0ull;
+    if (first_use_on_device(&attr_done)) {
         MMIF_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
-        attr_done = true;
     }
     dim3 grid(2 * S, N);
     hist_kernel<<<grid, kHT, sizeof(HistSmem), st>>>(a, b, f, P, S, counts, ws.hist_extra, ent, estride);

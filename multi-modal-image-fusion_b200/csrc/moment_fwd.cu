@@ -45,10 +45,9 @@ size_t fwd_ws_bytes(int win, int B, int H, int W) {
 template <int WIN, int EPI>
 static int launch_t(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& my, const FwdParams& p, dim3 grid,
                     cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0ull;
+    if (first_use_on_device(&attr_done)) {
         MMIF_CUDA(cudaFuncSetAttribute(moment_fwd_kernel<WIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF)));
-        attr_done = true;
     }
     moment_fwd_kernel<WIN, EPI><<<grid, kNT, sizeof(SmemF), st>>>(m1, m2, my, p);
     MMIF_CUDA(cudaGetLastError());
