@@ -32,7 +32,7 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
     BwdGeom g;
     g.Hout = H - (win - 1); g.Wout = W - (win - 1);
     g.nstrip = ceil_div(W, bwd_tg(win));
-    g.seg_rows = pick_seg_rows(H, B * g.nstrip, 2 * 148, 2 * (win - 1) + 8);   // 2 CTAs / SM; halo + batch rounding + prologue
+    g.seg_rows = pick_seg_rows(H, B * g.nstrip, 2 * 148, 2 * (win - 1) + 8, 0.72);   // 2 CTAs / SM; halo + batch rounding + prologue
     g.nseg = ceil_div(H, g.seg_rows);
     return g;
 }

@@ -7,7 +7,10 @@ namespace mmif {
 // Rows per segment (a multiple of 8) for `rows` rows split among CTAs that each pay `extra_rows` rows of
 // halo / prologue work, with `other_ctas` strips x samples and `slots` CTAs resident on the chip:
 // minimise  waves x (seg_rows + extra_rows)  where waves counts the quantised tail of the last wave.
-int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows) {
+// `tail` > 0 (backward kernels, measured): a last wave that fills at most half of the slots costs only `tail` of a full
+// one, because a CTA alone on its SM runs 1.39x faster than two sharing it; with it the model tracks a scan of forced
+// segment heights (64 .. 3072 rows, B = 8 and 64 of 3072x4096) to +-1 %.  tail == 0: the older, more pessimistic tail term.
+int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows, double tail) {
     int best_seg = 8;
     double best = 1e300;
     const int max_nseg = ceil_div(rows, 8);
@@ -15,7 +18,8 @@ int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows) {
         const int seg = ceil_div(ceil_div(rows, nseg), 8) * 8;
         if (ceil_div(rows, seg) != nseg) continue;
         const double w = (double)other_ctas * nseg / slots;
-        const double waves = fmax(ceil(w), w + 0.5);
+        const double frac = w - floor(w);
+        const double waves = tail > 0.0 ? floor(w) + (frac > 1e-9 ? (frac <= 0.5 ? tail : 1.0) : 0.0) : fmax(ceil(w), w + 0.5);
         const double cost = waves * (seg + extra_rows);
         if (cost < best) { best = cost; best_seg = seg; }
         if (seg <= 16) break;

@@ -373,7 +373,7 @@ struct FwdLaunch {
     float* maps[6];          // EPI_MAPS outputs
     unsigned char* denorm;   // do_sobel: uint8 image of y (or NULL)
 };
-int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows);
+int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows, double tail = 0.0);
 int fwd_seg_rows(int rows, int other_ctas);
 size_t fwd_ws_bytes(int win, int B, int H, int W);       // counters + partials (sums live elsewhere)
 // ws: zero-initialised workspace of fwd_ws_bytes; sums: B x sums_stride doubles (device).
