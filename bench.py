@@ -275,9 +275,12 @@ def main():
     if not args.no_extras:
         result['e2e'] = e2e_leg(args, dev, world, rank, ML, B)
         result['train_step_c2'] = train_step_leg(dev, world, rank, ML)
+        sharded = metric_suite_sharded_leg(dev, world, rank, MM) if world > 1 else None
         if rank == 0:
             result['torch_cuda_eager'] = torch_eager_leg(dev, ML, value)
             result['metric_suite'] = metric_suite_leg(dev, MM)
+            if sharded is not None:
+                result['metric_suite']['sharded_by_pair'] = sharded
         if world == 1:
             result['cpu_baseline'] = cpu_baseline_leg()
     else:
@@ -515,6 +518,48 @@ def train_step_leg(dev, world, rank, ML):
         8 * world, 'DDP over NCCL' if world > 1 else 'single process')
     res['global_mpix_per_step'] = 8 * world * 65536 / 1e6
     return res
+
+
+def metric_suite_sharded_leg(dev, world, rank, MM):
+    """BASELINE configs[3] / configs[2] over N GPUs: pairs i = rank (mod world) on each rank, one launch
+    per kernel family per rank, ONE all-gather of the (pairs/rank, 16) float64 rows; images resident in HBM.
+    Time per evaluation = max over ranks (device events around K evaluations, barrier on both sides)."""
+    import torch.distributed as dist
+    out = {}
+    for name, (n, h, w) in (('polar_32x1224x1024', (32, 1024, 1224)), ('tno_21x640x480', (21, 480, 640))):
+        g = torch.Generator(device=dev).manual_seed(7)              # same pairs on every rank, then this rank's shard
+        a = torch.randint(0, 256, (n, 1, h, w), device=dev, generator=g).float()
+        b = torch.randint(0, 256, (n, 1, h, w), device=dev, generator=g).float()
+        f = torch.floor((a + b) / 2)
+        mine = list(range(rank, n, world))
+        sa, sb, sf = (t[mine].contiguous() for t in (a, b, f))
+        del a, b, f
+        per = (n + world - 1) // world
+        pad = torch.zeros(per, 16, dtype=torch.float64, device=dev)
+        table = torch.empty(world * per, 16, dtype=torch.float64, device=dev)
+
+        def evaluate():
+            if mine:
+                pad[:len(mine)] = MM.eval_metrics_batch(sa, sb, sf)
+            dist.all_gather_into_tensor(table, pad)
+
+        for _ in range(3):
+            evaluate()
+        iters = 10
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            evaluate()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[name] = {'pairs_per_s': n / (ms.item() * 1e-3), 'ms_per_evaluation': ms.item(), 'pairs': n, 'pairs_per_rank': per,
+                     'collective': 'one all-gather of %d x 16 float64 rows per rank' % per}
+    return out
 
 
 def metric_suite_leg(dev, MM):
