@@ -335,3 +335,53 @@ def test_ssim_module_dict_is_differentiable(use_padding):
     d = ML.SSIM(11, 1.0).cuda()(A, F_)
     with pytest.raises(NotImplementedError):
         d['sigma'].sum().backward()
+
+
+def test_train_step_shape_through_a_network_matches_the_oracle():
+    """train.py:64-71 as a whole: imgf = model(img1, img2) (a non-leaf), the three drop-in losses, backward, clip, Adam.
+    The parameter gradients must equal those of the same network under the fp64 oracle loss; also with a NON-contiguous
+    imgf (channel 0 of a two-channel output)."""
+    ML = _mods()
+    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(31)
+    a, b = (torch.rand(2, 1, 48, 72, generator=g) for _ in range(2))
+
+    def make(dtype):
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(torch.nn.Conv2d(2, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 3, padding=1))
+        return net.to(dtype)
+
+    keep = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the test network must run in real fp32 to be comparable
+    try:
+        _train_step_cases(ML, make, a, b)
+    finally:
+        torch.backends.cudnn.allow_tf32 = keep
+
+
+def _train_step_cases(ML, make, a, b):
+    for slice_channel in (False, True):
+        net32 = make(torch.float32).cuda()
+        net64 = make(torch.float64)
+        A, B_ = a.cuda(), b.cuda()
+        out = net32(torch.cat([A, B_], dim=1))
+        imgf = out[:, :1] if slice_channel else out.sum(dim=1, keepdim=True)
+        assert imgf.is_contiguous() != slice_channel
+        loss = ML.SSIMLoss('ssim', weight=1.0)(A, B_, imgf) + ML.PixelLoss('l1', 0.01)(A, B_, imgf, mode='max') \
+            + ML.GradLoss('l1', 0.1)(A, B_, imgf, mode='max')
+        loss.backward()
+        o64 = net64(torch.cat([a, b], dim=1).double())
+        f64 = o64[:, :1] if slice_channel else o64.sum(dim=1, keepdim=True)
+        l64 = sum(OL.train_objective(a.double(), b.double(), f64))
+        l64.backward()
+        assert abs(loss.item() - l64.item()) <= 1e-5 * abs(l64.item())
+        for p32, p64 in zip(net32.parameters(), net64.parameters()):
+            if p64.grad is None:
+                assert p32.grad is None or float(p32.grad.abs().max()) == 0.0
+                continue
+            ref = p64.grad.numpy()
+            got = p32.grad.double().cpu().numpy()
+            assert np.abs(got - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-12), (slice_channel, np.abs(got - ref).max(), np.abs(ref).max())
+        opt = torch.optim.Adam(net32.parameters(), lr=1e-4)
+        torch.nn.utils.clip_grad_norm_(net32.parameters(), 5.0)
+        opt.step()
