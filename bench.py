@@ -562,6 +562,19 @@ def metric_suite_sharded_leg(dev, world, rank, MM):
     return out
 
 
+def eval_py_row(MM, a, b, f):
+    """The calls eval.py:29-75 makes for one pair, on the drop-in functions (CPU tensors in, python floats out: every
+    value is pulled with .item() like eval.py:52-68 does)."""
+    m = (MM.calc_mse(a, f) + MM.calc_mse(b, f)) * 0.5
+    q, n, l = MM.calc_Qabf(a, b, f, L=1.5, full=True)
+    vals = [MM.calc_std(f), MM.calc_ag(f), MM.calc_sf(f), m, MM.calc_psnr(m), (MM.calc_cc(a, f) + MM.calc_cc(b, f)) * 0.5,
+            MM.calc_scd(a, b, f), MM.calc_entropy(f), MM.calc_cross_ent(a, f) + MM.calc_cross_ent(b, f),
+            MM.calc_mul_info(a, f, normalized=True) + MM.calc_mul_info(b, f, normalized=True), q, n, l,
+            (MM.calc_ssim(a, f) + MM.calc_ssim(b, f)) * 0.5, (MM.calc_msssim(a, f) + MM.calc_msssim(b, f)) * 0.5,
+            MM.calc_viff(a, b, f, simple=False)]
+    return [v.item() for v in vals]
+
+
 def metric_suite_leg(dev, MM):
     """Second headline metric: full 16-metric suite, pairs/s (BASELINE configs[2] and configs[3] shapes).
     `pairs_per_s`: images resident in HBM (float32, as the reference's functions take them);
@@ -622,6 +635,15 @@ def metric_suite_leg(dev, MM):
 
         ms_f32, ms_u8 = timeit(e2e_f32, 5), timeit(e2e_u8, 5)
         ca, cb, cf_ = (t[:1].cpu() for t in (a, b, f))
+        # per-pair latency of the UNMODIFIED eval.py call pattern on the drop-in functions: CPU tensors in (uploaded once
+        # per image), ~25 separate calc_* calls, one .item() sync per metric
+        eval_py_row(MM, ca, cb, cf_)
+        host_pairs = [tuple(t[k % n:k % n + 1].cpu() for t in (a, b, f)) for k in range(1, 6)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for pa, pb, pf in host_pairs:
+            eval_py_row(MM, pa, pb, pf)
+        per_pair_ms = (time.perf_counter() - t0) / len(host_pairs) * 1e3
         torch.set_num_threads(os.cpu_count() or 1)
         t0 = time.perf_counter()
         OM.eval_pair(ca, cb, cf_)
@@ -631,6 +653,7 @@ def metric_suite_leg(dev, MM):
                      'hbm_frac_87.6B_per_pixel': 87.6 * n * h * w / (ms * 1e-3) / 1e9 / peak,
                      'e2e_f32_host_pairs_per_s': n / (ms_f32 * 1e-3), 'e2e_u8_host_pairs_per_s': n / (ms_u8 * 1e-3),
                      'h2d_bytes_f32': 12 * n * h * w, 'h2d_bytes_u8': 3 * n * h * w, 'd2h_bytes': n * 16 * 8,
+                     'eval_py_call_pattern_ms_per_pair': per_pair_ms,
                      'cpu_reference_pairs_per_s': 1.0 / cpu_s, 'cpu_cores': torch.get_num_threads(),
                      'cpu_sample': '1 pair, oracle port of eval.py:29-75, single run'}
     return out
