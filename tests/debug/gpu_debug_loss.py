@@ -1,6 +1,6 @@
 """Debug helper (GPU box): run the loss cases, print per-term errors and where they are."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'golden')]
 import numpy as np, torch
 import cases, gates
