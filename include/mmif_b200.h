@@ -116,6 +116,16 @@ int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f, int B, in
                      const float* gout1, const float* pair_w, int cs_only, float scale, float* dF,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* SSIM(win_size) of the loss module (loss.py:163-185 -> calc_ssim, loss.py:52-110, size_average=True) for a window of
+ * 11, 9, 7, 5 or 3 taps (sigma by the loss rule, loss.py:34): mmif_ssim_fwd_win writes the per-sample means
+ * ssim, cs, sigma of the pairs (i1, f), (i2, f) in the loss block layout (out: mmif_loss_out_doubles(B) doubles);
+ * mmif_ssim_bwd_ex_win is mmif_ssim_bwd_ex with that window.  ws from mmif_loss_workspace_bytes. */
+int mmif_ssim_fwd_win(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                      double* out, void* ws, size_t ws_bytes, void* stream);
+int mmif_ssim_bwd_ex_win(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                         const float* gout1, const float* pair_w, int cs_only, float scale, float* dF,
+                         void* ws, size_t ws_bytes, void* stream);
+
 /* One window size (11, 9, 7, 5 or 3; sigma by the loss rule, loss.py:34) of MSW_SSIM.forward
  * (loss.py:226-237): out_sums8[8*n] = sum over window positions of gamma*ssim(I1,If) + (1-gamma)*ssim(I2,If),
  * gamma = sigma1/(sigma1+sigma2) per position.  mmif_mswssim_bwd: dF (+)= gout1[0] * scale *

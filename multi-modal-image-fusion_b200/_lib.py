@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmmif_b200.so')
 SYMBOLS = [
     'mmif_version', 'mmif_last_error', 'mmif_check_device', 'mmif_set_gaussian_taps',
     'mmif_loss_workspace_bytes', 'mmif_loss_out_doubles', 'mmif_fusion_loss_fwd', 'mmif_fusion_loss_bwd',
-    'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
+    'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_ssim_fwd_win', 'mmif_ssim_bwd_ex_win', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
     'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_ssim',
     'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8',
     'mmif_eval_suite_u8', 'mmif_eval_suite_u8_host', 'mmif_norm_workspace_bytes', 'mmif_norm_loss', 'mmif_norm_loss_bwd', 'mmif_test_post',
@@ -63,6 +63,8 @@ def load():
     lib.mmif_tv_loss.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_tv_loss_bwd.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, vp]
     lib.mmif_ssim_bwd_ex.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, ci, cf, vp, vp, sz, vp]
+    lib.mmif_ssim_fwd_win.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
+    lib.mmif_ssim_bwd_ex_win.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, ci, cf, vp, vp, sz, vp]
     lib.mmif_mswssim_fwd.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_mswssim_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, vp, cf, ci, vp, vp, sz, vp]
     lib.mmif_halve.argtypes = [vp, ci, ci, ci, vp, vp]

@@ -135,7 +135,10 @@ def _fused(img1, img2, imgf, data_range=None, pixel=None, grad=None, w_ssim=None
     return _memo.lookup(img1, img2, imgf, cfg_key)
 
 
-def _fwd_per_sample(x1, x2, y, data_range):
+SSIM_WINDOWS = (11, 9, 7, 5, 3)     # windows the SSIM kernels are instantiated for (the MSW_SSIM set, loss.py:214)
+
+
+def _fwd_per_sample(x1, x2, y, data_range, win=11):
     """Fused forward (no gradient) -> (B, 6) float64 per-sample means: ssim1, cs1, sigma1, ssim2, cs2, sigma2."""
     lib = L.load()
     B, H, W = y.shape
@@ -146,13 +149,18 @@ def _fwd_per_sample(x1, x2, y, data_range):
     if nws == 0:
         raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11 at every level')
     ws = L.workspace(dev, nws, 'loss', (B, H, W))
+    if win != 11:
+        with torch.cuda.device(dev):
+            L.check(lib.mmif_ssim_fwd_win(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(win), float(data_range),
+                                          out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+        return out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
     with torch.cuda.device(dev):
         L.check(lib.mmif_fusion_loss_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(),
                                          None, ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
     return out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
 
 
-def _ssim_bwd_ex(x1, x2, y, data_range, gout1, pair_w, cs_only, scale):
+def _ssim_bwd_ex(x1, x2, y, data_range, gout1, pair_w, cs_only, scale, win=11):
     lib = L.load()
     B, H, W = y.shape
     dev = y.device
@@ -160,9 +168,9 @@ def _ssim_bwd_ex(x1, x2, y, data_range, gout1, pair_w, cs_only, scale):
     ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
     pw = pair_w.to(torch.float32).contiguous() if pair_w is not None else None
     with torch.cuda.device(dev):
-        L.check(lib.mmif_ssim_bwd_ex(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, float(data_range), gout1.data_ptr(),
-                                     pw.data_ptr() if pw is not None else None, int(cs_only), float(scale), dF.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+        L.check(lib.mmif_ssim_bwd_ex_win(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(win), float(data_range),
+                                         gout1.data_ptr(), pw.data_ptr() if pw is not None else None, int(cs_only), float(scale),
+                                         dF.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
     return dF
 
 
@@ -209,16 +217,16 @@ class _SSIMDict(torch.autograd.Function):
     source and the upstream per-sample gradients as pair weights; sigma = clamp(var(img1), 1e-4) does not depend on img2."""
 
     @staticmethod
-    def forward(ctx, img1, img2, data_range):
+    def forward(ctx, img1, img2, data_range, win=11):
         x, B, H, W = L.as_f32_3d(img1.detach(), 'img1')
         y, _, _, _ = L.as_f32_3d(img2.detach(), 'img2')
         if y.shape != x.shape:
             raise L.MmifError(f'shape mismatch: {tuple(img1.shape)} {tuple(img2.shape)}')
         L.ensure_device(x.device)
         x, y = x.view(B, H, W), y.view(B, H, W)
-        ps = _fwd_per_sample(x, x, y, data_range).to(torch.float32)
+        ps = _fwd_per_sample(x, x, y, data_range, win).to(torch.float32)
         ctx.save_for_backward(x, y)
-        ctx.data_range, ctx.shape1, ctx.shape2 = data_range, img1.shape, img2.shape
+        ctx.data_range, ctx.shape1, ctx.shape2, ctx.win = data_range, img1.shape, img2.shape, win
         ctx.set_materialize_grads(False)
         return ps[:, 0].clone(), ps[:, 1].clone(), ps[:, 2].clone()
 
@@ -233,7 +241,7 @@ class _SSIMDict(torch.autograd.Function):
                 if g is None:
                     continue
                 pw = torch.stack([g.to(torch.float32).reshape(-1), torch.zeros_like(g, dtype=torch.float32).reshape(-1)], dim=1)
-                d = _ssim_bwd_ex(src, src, tgt, ctx.data_range, one, pw, cs_only, 1.0)
+                d = _ssim_bwd_ex(src, src, tgt, ctx.data_range, one, pw, cs_only, 1.0, ctx.win)
                 out = d if out is None else out + d
             return out if out is not None else torch.zeros_like(tgt)
 
@@ -244,7 +252,7 @@ class _SSIMDict(torch.autograd.Function):
             if g_sigma is not None:
                 raise NotImplementedError("gradient of SSIM.forward()['sigma'] w.r.t. img1 is not built")
             g1 = wrt(y, x).view(ctx.shape1)
-        return g1, g2, None
+        return g1, g2, None, None
 
 
 def _pad_raw(x, pad):
@@ -463,24 +471,26 @@ def _auto_range(img):
 
 
 def _ssim_dict(img1, img2, data_range, use_padding, size_average, win_size=11):
+    """calc_ssim of the loss module with the module's own window (loss.py:52-110, 163-185): 11 taps, or 9 / 7 / 5 / 3
+    (sigma by loss.py:34) for SSIM(win_size=...)."""
+    if win_size not in SSIM_WINDOWS:
+        raise NotImplementedError(f'SSIM windows {SSIM_WINDOWS} are built, not {win_size}')
     if use_padding:
-        if win_size != 11:
-            raise NotImplementedError('only the 11-tap window of the training objective is built')
-        img1, img2 = _ReflectPad.apply(img1, 5), _ReflectPad.apply(img2, 5)
+        img1, img2 = _ReflectPad.apply(img1, win_size // 2), _ReflectPad.apply(img2, win_size // 2)
         use_padding = False
-    if win_size != 11:
-        raise NotImplementedError('only the 11-tap window of the training objective is built')
     if data_range is None:
         data_range = _auto_range(img1)
     needs_grad = torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad)
     if not size_average:
+        if win_size != 11:
+            raise NotImplementedError('SSIM maps (size_average=False) are built for the 11-tap window')
         if needs_grad:
             raise NotImplementedError('gradients through the SSIM maps (size_average=False) are not built')
         return ssim_maps(img1, img2, data_range)
-    if needs_grad:
+    if needs_grad or win_size != 11:
         for t, nm in ((img1, 'img1'), (img2, 'img2')):
             L.require_cuda(t, nm)
-        ss, cs, sg = _SSIMDict.apply(img1, img2, data_range)
+        ss, cs, sg = _SSIMDict.apply(img1, img2, data_range, win_size)
         return {'ssim': ss, 'cs': cs, 'sigma': sg}
     _, _, _, ps = _fused(img1, img1, img2, data_range=data_range)
     return {'ssim': ps[:, 0], 'cs': ps[:, 1], 'sigma': ps[:, 2]}

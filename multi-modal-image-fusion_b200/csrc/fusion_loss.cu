@@ -653,14 +653,30 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     return launch_bwd(i1, i2, f, B, H, W, cfg, gout3, dF_unit, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+static double loss_sigma_of(int win) { return win == 11 ? 1.5 : 0.15 * (win - 1); }     // loss.py:34
+static bool msw_win_ok(int win) { return win == 11 || win == 9 || win == 7 || win == 5 || win == 3; }
+
 /* d/dIf of  scale * sum_n sum_k pair_w[n][k] * mean_windows(S_k or cs_k)(I_k[n], If[n])  times the device
  * scalar gout1[0]: the building block of 'w-ssim' (loss.py:259-266, per-sample gamma) and of the
  * MS-SSIM levels (loss.py:140-158: cs on levels 0..3, ssim on level 4, per-sample chain-rule factors). */
+extern "C" int mmif_ssim_bwd_ex_win(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                                    const float* gout1, const float* pair_w, int cs_only, float scale, float* dF, void* ws,
+                                    size_t ws_bytes, void* stream);
+
 extern "C" int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f, int B, int H, int W, float data_range,
                                 const float* gout1, const float* pair_w, int cs_only, float scale, float* dF, void* ws,
                                 size_t ws_bytes, void* stream) {
-    int rc = check_common(i1, i2, f, B, H, W);
-    if (rc) return rc;
+    return mmif_ssim_bwd_ex_win(i1, i2, f, B, H, W, WIN11, data_range, gout1, pair_w, cs_only, scale, dF, ws, ws_bytes, stream);
+}
+
+/* The same for SSIM(win_size) of the loss module with win = 11, 9, 7, 5 or 3 (window sigma by the loss rule, loss.py:34). */
+extern "C" int mmif_ssim_bwd_ex_win(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                                    const float* gout1, const float* pair_w, int cs_only, float scale, float* dF, void* ws,
+                                    size_t ws_bytes, void* stream) {
+    if (!i1 || !i2 || !f) { set_error("null image pointer"); return MMIF_E_NULL; }
+    if (!msw_win_ok(win)) { set_error("SSIM window %d unsupported (11, 9, 7, 5, 3)", win); return MMIF_E_MODE; }
+    if (B < 1 || H < win || W < win) { set_error("shape (%d,%d,%d) smaller than the %d-tap window", B, H, W, win); return MMIF_E_SHAPE; }
+    if (((uintptr_t)i1 | (uintptr_t)i2 | (uintptr_t)f) & 3) { set_error("image pointers must be 4-byte aligned"); return MMIF_E_ALIGN; }
     if (!gout1 || !dF) { set_error("null gout1/dF"); return MMIF_E_NULL; }
     if (((uintptr_t)dF | (uintptr_t)pair_w) & 3) { set_error("dF / pair_w must be 4-byte aligned"); return MMIF_E_ALIGN; }
     MmifLossCfg cfg;
@@ -670,7 +686,29 @@ extern "C" int mmif_ssim_bwd_ex(const float* i1, const float* i2, const float* f
     BwdExtra ex;
     memset(&ex, 0, sizeof(ex));
     ex.pair_w = pair_w; ex.ssim_base = scale; ex.cs_only = cs_only; ex.do_sobel = 0; ex.use_base = true;
+    if (win != WIN11) { ex.win = win; ex.sigma = loss_sigma_of(win); }
     return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
+}
+
+/* calc_ssim(size_average=True) of the loss module for a window of 11, 9, 7, 5 or 3 taps (SSIM(win_size), loss.py:163-185;
+ * sigma by the loss rule): the per-sample means ssim, cs, sigma of the pairs (i1, f) and (i2, f) in the loss block
+ * layout (out[MMIF_LOSS_HEAD + 6 n ...]; the head holds 1 - mean ssim, 0, 0).  ws from mmif_loss_workspace_bytes. */
+extern "C" int mmif_ssim_fwd_win(const float* i1, const float* i2, const float* f, int B, int H, int W, int win, float data_range,
+                                 double* out, void* ws, size_t ws_bytes, void* stream) {
+    if (!i1 || !i2 || !f || !out) { set_error("null pointer"); return MMIF_E_NULL; }
+    if (!msw_win_ok(win)) { set_error("SSIM window %d unsupported (11, 9, 7, 5, 3)", win); return MMIF_E_MODE; }
+    if (B < 1 || H < win || W < win) { set_error("shape (%d,%d,%d) smaller than the %d-tap window", B, H, W, win); return MMIF_E_SHAPE; }
+    if (((uintptr_t)i1 | (uintptr_t)i2 | (uintptr_t)f) & 3) { set_error("image pointers must be 4-byte aligned"); return MMIF_E_ALIGN; }
+    const size_t core = loss_ws_core_bytes(B, H, W);
+    if (!core || !ws || ws_bytes < core + (size_t)B * 8 * sizeof(double)) { set_error("workspace too small"); return MMIF_E_WORKSPACE; }
+    FwdLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.win = win; L.sigma = loss_sigma_of(win); L.epi = EPI_SSIM; L.finalize = FIN_LOSS; L.do_sobel = 0;
+    L.data_range = data_range;
+    L.cfg.w_ssim = 1.f; L.cfg.data_range = data_range;
+    L.cfg.pixel_combine = L.cfg.grad_combine = MMIF_COMBINE_MAX; L.cfg.pixel_norm = L.cfg.grad_norm = MMIF_NORM_L1;
+    double* sums = (double*)((unsigned char*)ws + core);
+    return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, out, ws, core, (cudaStream_t)stream);
 }
 
 /* size_average=False of calc_ssim (loss.py:52-110, metric.py:316-364): the SSIM / CS / clamped-variance MAPS of the
@@ -710,8 +748,6 @@ extern "C" int mmif_test_post(const float* i1, const float* i2, const float* f, 
     return launch_moment_fwd(L, i1, i2, f, B, H, W, sums, 8, out, ws, core, (cudaStream_t)stream);
 }
 
-static double loss_sigma_of(int win) { return win == 11 ? 1.5 : 0.15 * (win - 1); }     // loss.py:34
-static bool msw_win_ok(int win) { return win == 11 || win == 9 || win == 7 || win == 5 || win == 3; }
 
 /* One window size of MSW_SSIM.forward (loss.py:226-237): out_sums[n] = sum over window positions of
  * gamma*ssim(I1,If) + (1-gamma)*ssim(I2,If), gamma = sigma1/(sigma1+sigma2) per position (device doubles,

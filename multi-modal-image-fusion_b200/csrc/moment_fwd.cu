@@ -91,6 +91,14 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
     if (!p.use_tma) { memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2)); memset(&my, 0, sizeof(my)); }
     dim3 grid(g.nstrip, g.nseg, B);
     if (L.epi == EPI_SSIM && L.win == 11) return launch_t<11, EPI_SSIM>(m1, m2, my, p, grid, st);
+    if (L.epi == EPI_SSIM && !L.do_sobel) {           // SSIM(win_size = 9, 7, 5, 3) of the loss module (loss.py:163-185)
+        switch (L.win) {
+            case 9: return launch_t<9, EPI_SSIM>(m1, m2, my, p, grid, st);
+            case 7: return launch_t<7, EPI_SSIM>(m1, m2, my, p, grid, st);
+            case 5: return launch_t<5, EPI_SSIM>(m1, m2, my, p, grid, st);
+            case 3: return launch_t<3, EPI_SSIM>(m1, m2, my, p, grid, st);
+        }
+    }
     if (L.epi == EPI_MAPS && L.win == 11) return launch_t<11, EPI_MAPS>(m1, m2, my, p, grid, st);
     if (L.epi == EPI_VIF) {
         switch (L.win) {

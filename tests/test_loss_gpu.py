@@ -121,7 +121,7 @@ def test_errors_match_reference():
         ML.PixelLoss('l3')(x, x, x, mode='max')
     assert ML.PixelLoss('l1')(x, x, x, mode='other') is None
     with pytest.raises(NotImplementedError):
-        ML.SSIM(win_size=7)(x, x)                        # only the 11-tap window of the objective is built
+        ML.SSIM(win_size=8)(x, x)                        # windows 11, 9, 7, 5, 3 are built
     with pytest.raises(NotImplementedError):
         ML.SSIMLoss('ssim')(x.clone().requires_grad_(True), x, x)   # gradients w.r.t. the sources
     with pytest.raises(Exception):
@@ -335,6 +335,44 @@ def test_ssim_module_dict_is_differentiable(use_padding):
     d = ML.SSIM(11, 1.0).cuda()(A, F_)
     with pytest.raises(NotImplementedError):
         d['sigma'].sum().backward()
+
+
+@pytest.mark.parametrize('win', [9, 7, 5, 3])
+@pytest.mark.parametrize('use_padding', [False, True])
+def test_ssim_module_other_window_sizes(win, use_padding):
+    """SSIM(win_size=9/7/5/3) (loss.py:163-185; window sigma 0.15 (win-1), loss.py:34): the per-sample dict against the
+    oracle, and the gradients of its 'ssim' / 'cs' entries w.r.t. both images against the fp64 oracle's autograd."""
+    ML = _mods()
+    a, _, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    w1 = torch.tensor([0.7, -1.3, 2.0])
+    w2 = torch.tensor([1.5, 0.25, -0.5])
+
+    def obj(d):
+        return (w1.to(d['ssim']) * d['ssim']).sum() + (w2.to(d['cs']) * d['cs']).sum()
+
+    mod = ML.SSIM(win, 1.0, use_padding).cuda()
+    assert tuple(mod.window.shape) == (1, 1, win, win)
+    with torch.no_grad():
+        d0 = mod(a.cuda(), f.cuda())
+    o32, o64 = OL.ssim(a, f, win, None, 1.0, use_padding), OL.ssim(a.double(), f.double(), win, None, 1.0, use_padding)
+    for key in ('ssim', 'cs', 'sigma'):
+        for n in range(3):
+            gates.assert_scalar(f'win{win}/{key}[{n}]', d0[key][n].item(), o32[key][n].item(), o64[key][n].item())
+    A, F_ = a.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+    val = obj(mod(A, F_))
+    gA, gF = torch.autograd.grad(val, (A, F_))
+    a64, f64 = a.double().requires_grad_(True), f.double().requires_grad_(True)
+    rA, rF = torch.autograd.grad(obj(OL.ssim(a64, f64, win, None, 1.0, use_padding)), (a64, f64))
+    a32, f32 = a.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    qA, qF = torch.autograd.grad(obj(OL.ssim(a32, f32, win, None, 1.0, use_padding)), (a32, f32))
+    for nm, got, r64, q32 in (('d/d img1', gA, rA, qA), ('d/d img2', gF, rF, qF)):
+        frac, mx, where = gates.grad_report(got.cpu().numpy(), r64.numpy())
+        ref_err = np.abs(q32.numpy() - r64.numpy()).max() / np.abs(r64.numpy()).max()
+        # gate: 1e-5 of max|g|, or (3-tap window, sigma 0.3: nearly a delta, tiny variances) 1.5x the band the reference's
+        # own fp32 graph keeps around the fp64 gradient — the same rule tests/gates.py applies to scalars
+        assert mx <= max(1e-5, 1.5 * ref_err), f'win {win} {nm}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+    with pytest.raises(NotImplementedError):
+        ML.SSIM(8, 1.0).cuda()(a.cuda(), f.cuda())
 
 
 def test_train_step_shape_through_a_network_matches_the_oracle():
