@@ -10,9 +10,11 @@ version), and a single autograd node with three outputs receives all three upstr
 Built on the same kernels: 'w-ssim' (per-sample gamma weights in the backward kernel), 'ms-ssim'
 (one SSIM forward/backward launch per pyramid level + pooling adjoints), use_padding=True (reflect-pad
 operator + its adjoint, applied per pyramid level / per window for 'ms-ssim' / 'msw-ssim'), size_average=False
-(SSIM / CS / sigma maps), data_range=None auto-detect, TVLoss and NormLoss forward/backward.  Not built (raise
-NotImplementedError, never a silent fallback): gradients w.r.t. the sources, gradients through SSIM.forward's dict.
-'msw-ssim' runs the same forward / backward kernels with the 11/9/7/5/3 windows and per-position weights.
+(SSIM / CS / sigma maps), data_range=None auto-detect, TVLoss and NormLoss forward/backward, SSIM(win_size) for the
+windows 11/9/7/5/3 with a dict that is differentiable w.r.t. both images ('ssim' and 'cs' entries).  'msw-ssim' runs the
+same forward / backward kernels with the 11/9/7/5/3 windows and per-position weights.  Not built (raise
+NotImplementedError, never a silent fallback): gradients of the fused objective w.r.t. the sources, the gradient of the
+dict's 'sigma' entry w.r.t. img1, gradients through the size_average=False maps, even or > 11-tap SSIM windows.
 """
 import ctypes
 import weakref
