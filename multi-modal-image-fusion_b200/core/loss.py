@@ -297,18 +297,19 @@ class _MSSSIM(torch.autograd.Function):
     4, per-sample chain-rule factors) + the padding and pooling adjoints."""
 
     @staticmethod
-    def forward(ctx, img1, img2, imgf, data_range, use_padding=False):
+    def forward(ctx, img1, img2, imgf, data_range, use_padding=False, win=11):
         x1, x2, y = _prep3(img1, img2, imgf)
         wts = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float32, device=y.device)
         levels, vals, ranges = [], [], []
+        pad = win // 2
         for lvl in range(5):
-            if min(y.shape[-2:]) < (6 if use_padding else 11):
-                raise L.MmifError(f'ms-ssim: level {lvl} is {tuple(y.shape[-2:])}, too small for the 11-tap window '
+            if min(y.shape[-2:]) < (pad + 1 if use_padding else win):
+                raise L.MmifError(f'ms-ssim: level {lvl} is {tuple(y.shape[-2:])}, too small for the {win}-tap window '
                                   '(the reference fails here too)')
-            lx1, lx2, ly = (_pad_raw(x1, 5), _pad_raw(x2, 5), _pad_raw(y, 5)) if use_padding else (x1, x2, y)
+            lx1, lx2, ly = (_pad_raw(x1, pad), _pad_raw(x2, pad), _pad_raw(y, pad)) if use_padding else (x1, x2, y)
             dr = _auto_range(x1) if data_range is None else data_range     # per level, from the level's img1 (loss.py:60-65)
             ranges.append(dr)
-            ps = _fwd_per_sample(lx1, lx2, ly, dr)
+            ps = _fwd_per_sample(lx1, lx2, ly, dr, win)
             vals.append(torch.stack([ps[:, 1], ps[:, 4]], dim=1) if lvl < 4 else torch.stack([ps[:, 0], ps[:, 3]], dim=1))
             levels.append((lx1, lx2, ly))
             if lvl < 4:
@@ -316,7 +317,7 @@ class _MSSSIM(torch.autograd.Function):
         v = torch.stack(vals, dim=0).to(torch.float32)              # (5, B, 2)
         vc = v.clamp(min=eps)
         ms = torch.prod(vc ** wts.view(5, 1, 1), dim=0)              # (B, 2)
-        ctx.levels, ctx.ranges, ctx.in_shape, ctx.use_padding = levels, ranges, imgf.shape, use_padding
+        ctx.levels, ctx.ranges, ctx.in_shape, ctx.use_padding, ctx.win = levels, ranges, imgf.shape, use_padding, win
         ctx.save_for_backward(v, vc, ms, wts)
         return ms[:, 0].contiguous(), ms[:, 1].contiguous()
 
@@ -331,13 +332,13 @@ class _MSSSIM(torch.autograd.Function):
         fac = g.unsqueeze(0) * wts.view(5, 1, 1) * ms.unsqueeze(0) / vc * (v >= eps).to(torch.float32)   # (5, B, 2)
         grads = []
         for lvl, (x1, x2, y) in enumerate(ctx.levels):
-            gl = _ssim_bwd_ex(x1, x2, y, ctx.ranges[lvl], one, fac[lvl], 1 if lvl < 4 else 0, 1.0)
-            grads.append(_pad_bwd_raw(gl, 5) if ctx.use_padding else gl)
+            gl = _ssim_bwd_ex(x1, x2, y, ctx.ranges[lvl], one, fac[lvl], 1 if lvl < 4 else 0, 1.0, ctx.win)
+            grads.append(_pad_bwd_raw(gl, ctx.win // 2) if ctx.use_padding else gl)
         for lvl in range(4, 0, -1):
             Bn, H, W = grads[lvl - 1].shape
             with torch.cuda.device(ms.device):
                 L.check(lib.mmif_halve_bwd(grads[lvl].data_ptr(), Bn, H, W, grads[lvl - 1].data_ptr(), L.stream_ptr(ms.device)))
-        return None, None, grads[0].view(ctx.in_shape), None, None
+        return None, None, grads[0].view(ctx.in_shape), None, None, None
 
 
 class _MSWSSIM(torch.autograd.Function):
@@ -545,11 +546,11 @@ class MS_SSIM(SSIM):
         self.register_buffer('weights', torch.FloatTensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333]))
 
     def forward(self, img1, img2):
-        if self.win_size != 11:
-            raise NotImplementedError('only the 11-tap window of the training objective is built')
+        if self.win_size not in SSIM_WINDOWS:
+            raise NotImplementedError(f'SSIM windows {SSIM_WINDOWS} are built, not {self.win_size}')
         if not self.size_average:
             raise NotImplementedError('size_average=False is not built yet')
-        return _MSSSIM.apply(img1, img1, img2, self.data_range, bool(self.use_padding))[0]
+        return _MSSSIM.apply(img1, img1, img2, self.data_range, bool(self.use_padding), int(self.win_size))[0]
 
 
 class MSW_SSIM(nn.Module):

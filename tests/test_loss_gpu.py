@@ -375,6 +375,32 @@ def test_ssim_module_other_window_sizes(win, use_padding):
         ML.SSIM(8, 1.0).cuda()(a.cuda(), f.cuda())
 
 
+@pytest.mark.parametrize('win,use_padding', [(7, False), (5, True)])
+def test_ms_ssim_module_other_window_sizes(win, use_padding):
+    """MS_SSIM(win_size=7/5) (loss.py:188-208 -> calc_msssim, loss.py:113-160, the module's window on every level):
+    per-sample values and the gradient w.r.t. the second image against the oracle."""
+    ML = _mods()
+    g = torch.Generator().manual_seed(77)
+    a, f = (torch.rand(2, 1, 208, 240, generator=g) for _ in range(2))
+    f = (0.6 * a + 0.4 * f).contiguous()
+    w = torch.tensor([1.0, -0.5])
+    mod = ML.MS_SSIM(win, 1.0, use_padding).cuda()
+    F_ = f.cuda().requires_grad_(True)
+    ms = mod(a.cuda(), F_)
+    o32 = OL.msssim(a, f, win, None, None, 1.0, use_padding)
+    f64 = f.double().requires_grad_(True)
+    o64 = OL.msssim(a.double(), f64, win, None, None, 1.0, use_padding)
+    for n in range(2):
+        gates.assert_scalar(f'ms-ssim win{win}[{n}]', ms[n].item(), o32[n].item(), o64[n].item())
+    (w.cuda() * ms).sum().backward()
+    (w.double() * o64).sum().backward()
+    f32 = f.clone().requires_grad_(True)
+    (w * OL.msssim(a, f32, win, None, None, 1.0, use_padding)).sum().backward()
+    frac, mx, where = gates.grad_report(F_.grad.cpu().numpy(), f64.grad.numpy())
+    ref_err = np.abs(f32.grad.numpy() - f64.grad.numpy()).max() / np.abs(f64.grad.numpy()).max()
+    assert mx <= max(1e-5, 1.5 * ref_err), f'win {win}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+
+
 def test_train_step_shape_through_a_network_matches_the_oracle():
     """train.py:64-71 as a whole: imgf = model(img1, img2) (a non-leaf), the three drop-in losses, backward, clip, Adam.
     The parameter gradients must equal those of the same network under the fp64 oracle loss; also with a NON-contiguous
