@@ -13,6 +13,9 @@ pytestmark = pytest.mark.gpu
 LG = np.load(cases.HERE + '/loss_golden.npz')
 
 
+WG = np.load(cases.HERE + '/ssim_windows_golden.npz')     # SSIM / MS_SSIM with 9/7/5/3-tap windows, from the real reference
+
+
 def _mods():
     import mmif_b200  # noqa: F401
     from mmif_b200.core import loss as ML
@@ -355,9 +358,11 @@ def test_ssim_module_other_window_sizes(win, use_padding):
     with torch.no_grad():
         d0 = mod(a.cuda(), f.cuda())
     o32, o64 = OL.ssim(a, f, win, None, 1.0, use_padding), OL.ssim(a.double(), f.double(), win, None, 1.0, use_padding)
-    for key in ('ssim', 'cs', 'sigma'):
+    g32, g64 = WG[f'ssim/win{win}/pad{int(use_padding)}/f32'], WG[f'ssim/win{win}/pad{int(use_padding)}/f64']    # real reference
+    for ki, key in enumerate(('ssim', 'cs', 'sigma')):
         for n in range(3):
             gates.assert_scalar(f'win{win}/{key}[{n}]', d0[key][n].item(), o32[key][n].item(), o64[key][n].item())
+            gates.assert_scalar(f'win{win}/{key}[{n}] vs golden', d0[key][n].item(), g32[ki, n], g64[ki, n])
     A, F_ = a.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
     val = obj(mod(A, F_))
     gA, gF = torch.autograd.grad(val, (A, F_))
@@ -390,8 +395,11 @@ def test_ms_ssim_module_other_window_sizes(win, use_padding):
     o32 = OL.msssim(a, f, win, None, None, 1.0, use_padding)
     f64 = f.double().requires_grad_(True)
     o64 = OL.msssim(a.double(), f64, win, None, None, 1.0, use_padding)
+    assert np.array_equal(a.numpy(), WG['ms/x']) and np.array_equal(f.numpy(), WG['ms/y'])      # the golden inputs
+    g32, g64 = WG[f'msssim/win{win}/pad{int(use_padding)}/f32'], WG[f'msssim/win{win}/pad{int(use_padding)}/f64']
     for n in range(2):
         gates.assert_scalar(f'ms-ssim win{win}[{n}]', ms[n].item(), o32[n].item(), o64[n].item())
+        gates.assert_scalar(f'ms-ssim win{win}[{n}] vs golden', ms[n].item(), g32[n], g64[n])
     (w.cuda() * ms).sum().backward()
     (w.double() * o64).sum().backward()
     f32 = f.clone().requires_grad_(True)

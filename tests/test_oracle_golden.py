@@ -118,3 +118,25 @@ def test_aggregate_quirk():
     vals = [0.0, 1.0, 2.0, 3.0]
     m = np.mean(vals)
     assert cols['sd'][0] == m and cols['sd'][1] == np.std([m] + vals) and cols['sd'][2:] == vals
+
+
+WG = np.load(cases.HERE + '/ssim_windows_golden.npz')
+
+
+@pytest.mark.parametrize('win', [9, 7, 5, 3])
+@pytest.mark.parametrize('pad', [False, True])
+def test_ssim_other_windows_pinned_to_the_reference(win, pad):
+    """SSIM(win_size=k) (loss.py:163-185; window sigma 0.15 (k-1), loss.py:34): oracle vs the real reference."""
+    a, _, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    for tag, dt, rtol in (('f32', torch.float32, 1e-6), ('f64', torch.float64, 1e-12)):
+        d = OL.ssim(a.to(dt), f.to(dt), win, None, 1.0, pad)
+        got = np.stack([d[k].numpy().astype(np.float64) for k in ('ssim', 'cs', 'sigma')])
+        np.testing.assert_allclose(got, WG[f'ssim/win{win}/pad{int(pad)}/{tag}'], rtol=rtol, atol=0)
+
+
+@pytest.mark.parametrize('win,pad', [(7, False), (5, True)])
+def test_msssim_other_windows_pinned_to_the_reference(win, pad):
+    x, y = T(WG['ms/x']), T(WG['ms/y'])
+    for tag, dt, rtol in (('f32', torch.float32, 1e-6), ('f64', torch.float64, 1e-12)):
+        got = OL.msssim(x.to(dt), y.to(dt), win, None, None, 1.0, pad).numpy().astype(np.float64)
+        np.testing.assert_allclose(got, WG[f'msssim/win{win}/pad{int(pad)}/{tag}'], rtol=rtol, atol=0)
