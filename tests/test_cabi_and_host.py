@@ -57,6 +57,14 @@ def test_argument_validation_without_gpu():
     assert lib.mmif_loss_out_doubles(3) == 4 + 18
     assert lib.mmif_metric_workspace_bytes(21, 480, 640) > 21 * (3 * 256 + 2 * 65536) * 4
     assert lib.mmif_set_gaussian_taps(18, 1.5, (ctypes.c_float * 18)()) == -2
+    # SSIM(win_size) entries: window set, shape against the window, null pointers, workspace
+    assert lib.mmif_ssim_fwd_win(None, None, None, 1, 32, 32, 7, 1.0, None, None, 0, None) == -1
+    assert lib.mmif_ssim_fwd_win(16, 16, 16, 1, 32, 32, 8, 1.0, 16, 16, 0, None) == -3            # even window
+    assert b'window' in lib.mmif_last_error()
+    assert lib.mmif_ssim_fwd_win(16, 16, 16, 1, 4, 32, 5, 1.0, 16, 16, 0, None) == -2             # H < window
+    assert lib.mmif_ssim_fwd_win(16, 16, 16, 1, 32, 32, 5, 1.0, 16, 16, 0, None) == -4            # workspace too small
+    assert lib.mmif_ssim_bwd_ex_win(16, 16, 16, 1, 32, 32, 13, 1.0, 16, None, 0, 1.0, 16, 16, 0, None) == -3
+    assert lib.mmif_ssim_bwd_ex_win(16, 16, 16, 1, 32, 32, 7, 1.0, None, None, 0, 1.0, 16, 16, 0, None) == -1
 
 
 def test_dropin_surface_and_error_behaviour():
