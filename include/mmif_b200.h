@@ -74,6 +74,25 @@ enum {
     MMIF_LOSS_PER_SAMPLE = 6 /* ssim1, cs1, sigma1, ssim2, cs2, sigma2 — the dict of SSIM.forward (loss.py:105-110) */
 };
 
+/* Launch bookkeeping (host side, process-wide, monotonically increasing): which kernels the library has enqueued.
+ * Lets a caller (and the parity tests) verify WHICH path served a call — e.g. that SSIMLoss + PixelLoss + GradLoss
+ * with a gradient wanted ran the single-pass loss+gradient kernel — and is what bench.py's `gpu_launches` counts. */
+enum {
+    MMIF_CNT_LOSS_FWD = 0,         /* moment_fwd_kernel<11, SSIM> with the pixel / Sobel terms: forward of the two-kernel path */
+    MMIF_CNT_LOSS_SINGLE_PASS = 1, /* fusion_loss_bwd_kernel<11, *, ZMODE=1, 0>: loss values AND dL/dIf in one launch */
+    MMIF_CNT_LOSS_BWD = 2,         /* fusion_loss_bwd_kernel<11, *, 0, 0>: recomputing backward */
+    MMIF_CNT_RESCALE = 3,          /* rescale_unit_kernel (backward of the single-pass path) */
+    MMIF_CNT_SSIM_BWD_EXT = 4,     /* SSIM-only backward launches (w-ssim, MS-SSIM levels, MSW-SSIM windows, SSIM dict) */
+    MMIF_CNT_MOMENT_FWD = 5,       /* every other moment_fwd_kernel launch (SSIM windows, maps, VIF scales, MSW) */
+    MMIF_CNT_METRIC = 6,           /* metric-suite kernels other than moment_fwd (pixel metrics, histograms, pyramids) */
+    MMIF_CNT_AUX = 7,              /* small operators: pad / halve / widen / norm / tv and their adjoints */
+    MMIF_CNT_TMAP_ENCODE = 8,      /* cuTensorMapEncodeTiled calls (not a launch) */
+    MMIF_CNT_TMAP_HIT = 9,         /* tensor maps served from the per-thread memo (not a launch) */
+    MMIF_CNT_N = 16
+};
+/* out[i] = counter i for i < n (HOST memory). */
+int mmif_launch_counts(unsigned long long* out, int n);
+
 int mmif_version(void);
 const char* mmif_last_error(void);
 /* 0 if device `dev` is usable by this library (compute capability 10.x). */
@@ -91,7 +110,8 @@ size_t mmif_loss_out_doubles(int B);
 
 /* Replaces SSIMLoss('ssim').forward + PixelLoss.forward + GradLoss.forward (loss.py:252-257,
  * 294-304, 330-344) and the SSIM.forward dict (loss.py:179-185) in one launch.
- * i1,i2,f: [B][H][W]; out: mmif_loss_out_doubles(B) doubles; dF_unit: [B][H][W] or NULL. */
+ * i1,i2,f: [B][H][W]; out: mmif_loss_out_doubles(B) doubles = the MMIF_LOSS_* block of 4 + 6 B doubles followed by
+ * its float32 mirror (same indices, at (float*)(out + 4 + 6 B)); dF_unit: [B][H][W] or NULL. */
 int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
                          const MmifLossCfg* cfg, double* out, float* dF_unit,
                          void* ws, size_t ws_bytes, void* stream);
@@ -107,6 +127,13 @@ int mmif_fusion_loss_fwd(const float* i1, const float* i2, const float* f, int B
 int mmif_fusion_loss_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W,
                          const MmifLossCfg* cfg, const float* gout3, const float* dF_unit, float* dF,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* The same, with the three upstream gradients as separate DEVICE scalars exactly as autograd hands them to the node
+ * (train.py:69-71: total = l1 + l2 + l3; total.backward()).  A NULL pointer means that loss value received no
+ * gradient (0); at least one must be non-NULL. */
+int mmif_fusion_loss_bwd3(const float* i1, const float* i2, const float* f, int B, int H, int W,
+                          const MmifLossCfg* cfg, const float* g_ssim, const float* g_pixel, const float* g_grad,
+                          const float* dF_unit, float* dF, void* ws, size_t ws_bytes, void* stream);
 
 /* d/dIf of  scale * sum_n sum_k pair_w[n][k] * mean_windows(S_k)(I_k[n], If[n]),  S = ssim or (cs_only) the
  * contrast-structure term, times the device scalar gout1[0].  pair_w: [B][2] device floats or NULL (= 1).

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmmif_b200.so')
 SYMBOLS = [
     'mmif_version', 'mmif_last_error', 'mmif_check_device', 'mmif_set_gaussian_taps',
     'mmif_loss_workspace_bytes', 'mmif_loss_out_doubles', 'mmif_fusion_loss_fwd', 'mmif_fusion_loss_bwd',
+    'mmif_fusion_loss_bwd3', 'mmif_launch_counts',
     'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_ssim_fwd_win', 'mmif_ssim_bwd_ex_win', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
     'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_ssim',
     'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8',
@@ -60,6 +61,8 @@ def load():
     lib.mmif_loss_out_doubles.argtypes = [ci]
     lib.mmif_fusion_loss_fwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, sz, vp]
     lib.mmif_fusion_loss_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, sz, vp]
+    lib.mmif_fusion_loss_bwd3.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.mmif_launch_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ci]
     lib.mmif_tv_loss.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_tv_loss_bwd.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, vp]
     lib.mmif_ssim_bwd_ex.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, ci, cf, vp, vp, sz, vp]
@@ -106,6 +109,36 @@ def stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def stream_int(device):
+    """cudaStream_t of torch's current stream on `device`, as a plain int."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def call(device, fn, *args):
+    """Run a library entry with `device` current (kernel launches go to the current device) and check its code."""
+    if torch.cuda.current_device() == (device.index if device.index is not None else torch.cuda.current_device()):
+        rc = fn(*args)
+    else:
+        with torch.cuda.device(device):
+            rc = fn(*args)
+    if rc != 0:
+        check(rc)
+
+
+def launch_counts():
+    """dict of the library's launch counters (include/mmif_b200.h MMIF_CNT_*)."""
+    buf = (ctypes.c_ulonglong * 16)()
+    check(load().mmif_launch_counts(buf, 16))
+    names = ('loss_fwd', 'loss_single_pass', 'loss_bwd', 'rescale', 'ssim_bwd_ext', 'moment_fwd', 'metric', 'aux',
+             'tmap_encode', 'tmap_hit')
+    return {n: int(buf[i]) for i, n in enumerate(names)}
+
+
+def kernel_launches(before, after):
+    """Number of kernels launched between two launch_counts() snapshots."""
+    return sum(after[k] - before[k] for k in after if not k.startswith('tmap'))
+
+
 def require_cuda(t, name='tensor'):
     if not t.is_cuda:
         raise MmifError(f'{name} must be a CUDA tensor (no CPU compute path exists)')
@@ -125,11 +158,11 @@ _ws_cache = {}
 _WS_CACHE_CAP = 16
 
 
-def workspace(device, nbytes, tag, shape=None):
+def workspace(device, nbytes, tag, shape=None, stream=None):
     """Zero-initialised workspace, cached per (device, stream, tag, shape).  The kernels leave their
     counters zeroed, but the carve-up of a workspace depends on the problem shape, so a buffer is
     only ever reused for the shape it was first zeroed for (small LRU)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag, shape)
+    key = (device.index, stream if stream is not None else torch.cuda.current_stream(device).cuda_stream, tag, shape)
     buf = _ws_cache.pop(key, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -17,6 +17,7 @@ NotImplementedError, never a silent fallback): gradients of the fused objective 
 dict's 'sigma' entry w.r.t. img1, gradients through the size_average=False maps, even or > 11-tap SSIM windows.
 """
 import ctypes
+import threading
 import weakref
 
 import torch
@@ -38,15 +39,45 @@ def _cfg(data_range, pixel_combine, grad_combine, pixel_norm, grad_norm, w_ssim=
     return c
 
 
+_cfg_structs = {}
+
+
+def _cfg_ref(cfg_key, want_grad):
+    """(struct, byref) for a configuration: built once — a training loop presents the same one every step."""
+    k = (cfg_key, want_grad)
+    hit = _cfg_structs.get(k)
+    if hit is None:
+        c = _cfg(*cfg_key)
+        c.want_grad = 1 if want_grad else 0
+        hit = _cfg_structs[k] = (c, ctypes.byref(c))
+        if len(_cfg_structs) > 256:
+            _cfg_structs.pop(next(iter(_cfg_structs)))
+    return hit
+
+
+_ws_bytes = {}
+
+
+def _loss_ws(lib, dev, stream, B, H, W):
+    n = _ws_bytes.get((B, H, W))
+    if n is None:
+        n = _ws_bytes[(B, H, W)] = lib.mmif_loss_workspace_bytes(B, H, W)
+    if n == 0:
+        raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11')
+    return L.workspace(dev, n, 'loss', (B, H, W), stream)
+
+
 class _FusedObjective(torch.autograd.Function):
     """(img1, img2, imgf) -> (w1 (1 - mean ssim), w2 pixel norm, w3 grad norm, per-sample ssim dict block).
 
-    When imgf needs a gradient the forward runs the single-pass kernel (loss values AND
-    d(l1+l2+l3)/d imgf in one launch); backward then only rescales that buffer if the three upstream
-    gradients are equal — decided on the device, so there is no host sync — and recomputes otherwise."""
+    `want_grad` is decided by the CALLER (`_Memo.lookup`), where the user's grad mode is visible — inside
+    `Function.forward` grad mode is always off.  With it the forward runs the single-pass kernel (loss values AND
+    d(l1+l2+l3)/d imgf in one launch); backward then only rescales that buffer if the three upstream gradients are
+    equal — decided on the device, so there is no host sync — and recomputes otherwise (unequal upstream, or the
+    second backward of a retained graph: the buffer is handed to autograd by the first)."""
 
     @staticmethod
-    def forward(ctx, img1, img2, imgf, cfg_key):
+    def forward(ctx, img1, img2, imgf, cfg_key, want_grad):
         lib = L.load()
         x1, B, H, W = L.as_f32_3d(img1, 'img1')
         x2, _, _, _ = L.as_f32_3d(img2, 'img2')
@@ -55,26 +86,24 @@ class _FusedObjective(torch.autograd.Function):
             raise L.MmifError(f'shape mismatch: {tuple(img1.shape)} {tuple(img2.shape)} {tuple(imgf.shape)}')
         dev = y.device
         L.ensure_device(dev)
-        cfg = _cfg(*cfg_key)
-        want_grad = bool(imgf.requires_grad and torch.is_grad_enabled() and SINGLE_PASS)
-        cfg.want_grad = 1 if want_grad else 0
+        want_grad = bool(want_grad and ctx.needs_input_grad[2])
+        _, cref = _cfg_ref(cfg_key, want_grad)
         dF_unit = torch.empty_like(y) if want_grad else None
-        out = torch.empty(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device=dev)
-        nws = lib.mmif_loss_workspace_bytes(B, H, W)
-        if nws == 0:
-            raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11')
-        ws = L.workspace(dev, nws, 'loss', (B, H, W))
-        with torch.cuda.device(dev):
-            L.check(lib.mmif_fusion_loss_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),
-                                             out.data_ptr(), dF_unit.data_ptr() if want_grad else None,
-                                             ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+        nd = L.LOSS_HEAD + L.LOSS_PER_SAMPLE * B
+        out = torch.empty(nd + (nd + 1) // 2, dtype=torch.float64, device=dev)
+        stream = L.stream_int(dev)
+        ws = _loss_ws(lib, dev, stream, B, H, W)
+        L.call(dev, lib.mmif_fusion_loss_fwd, x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, cref, out.data_ptr(),
+               dF_unit.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel(), stream)
         ctx.save_for_backward(x1, x2, y)
         ctx.dF_unit = dF_unit
+        ctx.single_pass = want_grad          # which kernel served the forward (the tests assert on it)
         ctx.cfg_key, ctx.dims, ctx.in_shape = cfg_key, (B, H, W), imgf.shape
-        vals = out[:3].to(torch.float32)
-        per_sample = out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE).to(torch.float32)
+        ctx.set_materialize_grads(False)
+        out32 = out[nd:].view(torch.float32)          # the kernel's own float32 mirror of the block: no conversion launches
+        per_sample = out32[L.LOSS_HEAD:nd].view(B, L.LOSS_PER_SAMPLE)
         ctx.mark_non_differentiable(per_sample)
-        return vals[0], vals[1], vals[2], per_sample
+        return out32[0], out32[1], out32[2], per_sample
 
     @staticmethod
     def backward(ctx, g_ssim, g_pix, g_grad, _g_ps):
@@ -82,26 +111,35 @@ class _FusedObjective(torch.autograd.Function):
         x1, x2, y = ctx.saved_tensors
         B, H, W = ctx.dims
         dev = y.device
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
-        g = torch.stack([zero if t is None else t.to(torch.float32).reshape(()) for t in (g_ssim, g_pix, g_grad)])
-        cfg = _cfg(*ctx.cfg_key)
+        ups, ptrs = [], []
+        for g in (g_ssim, g_pix, g_grad):       # device scalars as autograd hands them over: no stack / zeros launches
+            if g is None:
+                ptrs.append(None)
+                continue
+            if g.dtype != torch.float32 or g.device != dev:
+                g = g.to(device=dev, dtype=torch.float32)
+            g = g.contiguous()
+            ups.append(g)
+            ptrs.append(g.data_ptr())
+        if not ups:
+            return None, None, torch.zeros(ctx.in_shape, dtype=torch.float32, device=dev), None, None
+        _, cref = _cfg_ref(ctx.cfg_key, False)
         # The single-pass buffer is consumed by the first backward: it is rescaled IN PLACE (nothing to do at all for
         # the unit upstream of total.backward()) and handed to autograd; a second backward (retain_graph) recomputes.
         unit, ctx.dF_unit = ctx.dF_unit, None
         dF = unit if unit is not None else torch.empty_like(y)
-        ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
-        with torch.cuda.device(dev):
-            L.check(lib.mmif_fusion_loss_bwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg),
-                                             g.data_ptr(), unit.data_ptr() if unit is not None else None, dF.data_ptr(),
-                                             ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
-        return None, None, dF.view(ctx.in_shape), None
+        stream = L.stream_int(dev)
+        ws = _loss_ws(lib, dev, stream, B, H, W)
+        L.call(dev, lib.mmif_fusion_loss_bwd3, x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, cref, ptrs[0], ptrs[1],
+               ptrs[2], unit.data_ptr() if unit is not None else None, dF.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        return None, None, dF.view(ctx.in_shape), None, None
 
 
 SINGLE_PASS = True   # set False to force the two-kernel (forward, then recomputing backward) path
 
 
-class _Memo:
-    """One-entry memo so loss_fn1/2/3 called back to back (train.py:64-68) cost one launch."""
+class _Memo(threading.local):
+    """One-entry memo PER THREAD so loss_fn1/2/3 called back to back (train.py:64-68) cost one launch."""
 
     def __init__(self):
         self.key, self.refs, self.value = None, None, None
@@ -110,13 +148,14 @@ class _Memo:
                      'w_ssim': 1.0, 'w_pixel': 0.01, 'w_grad': 0.1}
 
     def lookup(self, img1, img2, imgf, cfg_key):
+        want_grad = bool(SINGLE_PASS and imgf.requires_grad and torch.is_grad_enabled())    # the CALLER's grad mode
         key = (img1.data_ptr(), img1._version, img2.data_ptr(), img2._version, imgf.data_ptr(), imgf._version,
-               tuple(imgf.shape), imgf.device, cfg_key, imgf.requires_grad and torch.is_grad_enabled(), SINGLE_PASS)
+               imgf.shape, imgf.device, cfg_key, imgf.requires_grad and torch.is_grad_enabled(), want_grad)
         if self.key == key and all(r() is t for r, t in zip(self.refs, (img1, img2, imgf))):
             return self.value
         if img1.requires_grad or img2.requires_grad:
             raise NotImplementedError('gradients w.r.t. the source images are not built (train.py never needs them)')
-        value = _FusedObjective.apply(img1, img2, imgf, cfg_key)
+        value = _FusedObjective.apply(img1, img2, imgf, cfg_key, want_grad)
         self.key, self.value = key, value
         self.refs = tuple(weakref.ref(t) for t in (img1, img2, imgf))
         return value
@@ -126,13 +165,22 @@ _memo = _Memo()
 
 
 def _fused(img1, img2, imgf, data_range=None, pixel=None, grad=None, w_ssim=None, w_pixel=None, w_grad=None):
-    for t, nm in ((img1, 'img1'), (img2, 'img2'), (imgf, 'imgf')):
-        L.require_cuda(t, nm)
+    if not (img1.is_cuda and img2.is_cuda and imgf.is_cuda):
+        for t, nm in ((img1, 'img1'), (img2, 'img2'), (imgf, 'imgf')):
+            L.require_cuda(t, nm)
     h = _memo.hint
-    for k, v in (('data_range', data_range), ('pixel', pixel), ('grad', grad), ('w_ssim', w_ssim), ('w_pixel', w_pixel),
-                 ('w_grad', w_grad)):
-        if v is not None:
-            h[k] = float(v) if not isinstance(v, tuple) else v
+    if data_range is not None:
+        h['data_range'] = float(data_range)
+    if pixel is not None:
+        h['pixel'] = pixel
+    if grad is not None:
+        h['grad'] = grad
+    if w_ssim is not None:
+        h['w_ssim'] = float(w_ssim)
+    if w_pixel is not None:
+        h['w_pixel'] = float(w_pixel)
+    if w_grad is not None:
+        h['w_grad'] = float(w_grad)
     cfg_key = (h['data_range'], h['pixel'][0], h['grad'][0], h['pixel'][1], h['grad'][1], h['w_ssim'], h['w_pixel'], h['w_grad'])
     return _memo.lookup(img1, img2, imgf, cfg_key)
 
@@ -141,25 +189,19 @@ SSIM_WINDOWS = (11, 9, 7, 5, 3)     # windows the SSIM kernels are instantiated 
 
 
 def _fwd_per_sample(x1, x2, y, data_range, win=11):
-    """Fused forward (no gradient) -> (B, 6) float64 per-sample means: ssim1, cs1, sigma1, ssim2, cs2, sigma2."""
+    """SSIM-only forward (no gradient, no pixel / Sobel terms) -> (B, 6) float64 per-sample means:
+    ssim1, cs1, sigma1, ssim2, cs2, sigma2."""
     lib = L.load()
     B, H, W = y.shape
     dev = y.device
-    cfg = _cfg(data_range, 'max', 'max', 'l1', 'l1')
     out = torch.empty(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device=dev)
     nws = lib.mmif_loss_workspace_bytes(B, H, W)
     if nws == 0:
         raise L.MmifError(f'unsupported shape {(B, H, W)}: H and W must be >= 11 at every level')
     ws = L.workspace(dev, nws, 'loss', (B, H, W))
-    if win != 11:
-        with torch.cuda.device(dev):
-            L.check(lib.mmif_ssim_fwd_win(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(win), float(data_range),
-                                          out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
-        return out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
-    with torch.cuda.device(dev):
-        L.check(lib.mmif_fusion_loss_fwd(x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(),
-                                         None, ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
-    return out[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
+    L.call(dev, lib.mmif_ssim_fwd_win, x1.data_ptr(), x2.data_ptr(), y.data_ptr(), B, H, W, int(win), float(data_range),
+           out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_int(dev))
+    return out[L.LOSS_HEAD:L.LOSS_HEAD + B * L.LOSS_PER_SAMPLE].view(B, L.LOSS_PER_SAMPLE)
 
 
 def _ssim_bwd_ex(x1, x2, y, data_range, gout1, pair_w, cs_only, scale, win=11):

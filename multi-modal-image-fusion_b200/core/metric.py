@@ -394,7 +394,7 @@ def test_post_step(img1, img2, imgf, data_range=1.0, want_image=True):
         L.check(lib.mmif_test_post(imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, float(data_range),
                                    out.data_ptr(), img8.data_ptr() if want_image else None, ws.data_ptr(), ws.numel(),
                                    L.stream_ptr(dev)))
-    ps = out[L.LOSS_HEAD:].view(n, L.LOSS_PER_SAMPLE)
+    ps = out[L.LOSS_HEAD:L.LOSS_HEAD + n * L.LOSS_PER_SAMPLE].view(n, L.LOSS_PER_SAMPLE)
     return ((ps[:, 0] + ps[:, 3]) * 0.5).to(torch.float32), img8
 
 

@@ -25,7 +25,11 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // Encode a 3-D (W,H,N) float32 tensor map with a (box_w, box_h, 1) box; false if TMA cannot be
 // used for this tensor (row pitch or base not 16-byte aligned, driver entry point missing).
+// Encodings are memoised per thread on (base, N, H, W, box): a training loop re-encodes nothing.
 bool make_tensor_map(CUtensorMap* map, const float* base, int N, int H, int W, int box_w, int box_h);
+
+// Launch bookkeeping behind mmif_launch_counts (include/mmif_b200.h MMIF_CNT_*): one relaxed atomic add per launch.
+void count_launch(int which, unsigned long long n = 1ull);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

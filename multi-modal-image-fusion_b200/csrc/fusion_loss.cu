@@ -41,7 +41,8 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
 struct BwdParams {
     const float* x1; const float* x2; const float* y;
     float* dF;
-    const float* gout;       // 3 upstream gradients (device)
+    const float* gout[3];    // upstream gradients of the three loss values (device scalars; all NULL = unit upstream;
+                             // gout[0] set and gout[1] / gout[2] NULL = those two terms get no gradient)
     int B, H, W, Hout, Wout;
     int seg_rows, nseg, nstrip;
     Taps taps;
@@ -89,6 +90,16 @@ __global__ void __launch_bounds__(kNT, 2)
 fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                        const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
     constexpr int HALO = BG<WIN>::HALO, kOFF = BG<WIN>::OFF, kVOFF = BG<WIN>::VOFF, kTG = BG<WIN>::TG, kWC = BG<WIN>::WC;
+    const bool unit_up = (p.gout[0] == nullptr) && (p.gout[1] == nullptr) && (p.gout[2] == nullptr);
+    const float g_ssim = unit_up ? 1.f : (p.gout[0] ? __ldg(p.gout[0]) : 0.f);
+    const float g_pix = unit_up ? 1.f : ((p.gout[1] && p.do_sobel) ? __ldg(p.gout[1]) : 0.f);
+    const float g_grad = unit_up ? 1.f : ((p.gout[2] && p.do_sobel) ? __ldg(p.gout[2]) : 0.f);
+    if (!ZMODE && p.dF_unit != nullptr && g_ssim == g_pix && g_pix == g_grad) {
+        // total = l1 + l2 + l3 (train.py:69): the upstream gradients are one common scalar, and the
+        // single-pass forward already produced d(total)/dIf for unit upstream: rescale_unit_kernel
+        // (launched just before this kernel) has rescaled it, nothing to recompute.
+        return;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemBwd& sb = *reinterpret_cast<SmemBwd*>(smem_raw);
     SmemB& sm = sb.s;
@@ -113,15 +124,6 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
     __syncthreads();
     const Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, R0, iend - R0 + HALO, jw0, p.taps);
-    const bool rd3 = p.gout && p.do_sobel;       // the SSIM-only entry passes a single upstream scalar
-    const float g_ssim = p.gout ? __ldg(p.gout + 0) : 1.f, g_pix = rd3 ? __ldg(p.gout + 1) : (p.gout ? 0.f : 1.f),
-                g_grad = rd3 ? __ldg(p.gout + 2) : (p.gout ? 0.f : 1.f);
-    if (!ZMODE && p.dF_unit != nullptr && g_ssim == g_pix && g_pix == g_grad) {
-        // total = l1 + l2 + l3 (train.py:69): the upstream gradients are one common scalar, and the
-        // single-pass forward already produced d(total)/dIf for unit upstream: rescale_unit_kernel
-        // (launched just before this kernel) has rescaled it, nothing to recompute.
-        return;
-    }
     const float npx = (float)p.B * (float)p.H * (float)p.W;
     const float k_ssim2 = 2.f * g_ssim * p.ssim_base / ((float)p.Hout * (float)p.Wout);   // the blurred coefficients are halved
     const float2 pairw = (EXT && p.pair_w) ? f2(__ldg(p.pair_w + 2 * n), __ldg(p.pair_w + 2 * n + 1)) : f2(1.f, 1.f);
@@ -464,8 +466,9 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
 // Companion of the early exit above: dF = g * dF_unit when the three upstream gradients are equal,
 // nothing otherwise (the recomputing kernel then does the work).  Pure streaming, 8 B/pixel.
 __global__ void __launch_bounds__(256)
-rescale_unit_kernel(const float* __restrict__ gout, const float* __restrict__ unit, float* __restrict__ dF, size_t n, int vec) {
-    const float g0 = __ldg(gout + 0), g1 = __ldg(gout + 1), g2 = __ldg(gout + 2);
+rescale_unit_kernel(const float* __restrict__ gs, const float* __restrict__ gp, const float* __restrict__ gg,
+                    const float* __restrict__ unit, float* __restrict__ dF, size_t n, int vec) {
+    const float g0 = gs ? __ldg(gs) : 0.f, g1 = gp ? __ldg(gp) : 0.f, g2 = gg ? __ldg(gg) : 0.f;
     if (!(g0 == g1 && g1 == g2)) return;
     if (unit == dF && g0 == 1.f) return;          // in place with unit upstream (total.backward()): the buffer already is dL/dIf
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -531,18 +534,20 @@ extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
     const size_t f = loss_ws_core_bytes(B, H, W);
     return f ? f + (size_t)B * 8 * sizeof(double) : 0;
 }
-extern "C" size_t mmif_loss_out_doubles(int B) { return (size_t)MMIF_LOSS_HEAD + (size_t)(B > 0 ? B : 0) * MMIF_LOSS_PER_SAMPLE; }
+extern "C" size_t mmif_loss_out_doubles(int B) { const size_t nd = loss_block_doubles(B); return nd + (nd + 1) / 2; }
 
 struct BwdExtra { const float* pair_w; float ssim_base; int cs_only; int do_sobel; bool use_base; int win; double sigma; int msw; int accum; };
 
+struct Upstream { const float* g[3]; };
 static int launch_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, const MmifLossCfg* cfg,
-                      const float* gout3, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
+                      const Upstream& up, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
                       cudaStream_t st, const BwdExtra* ex = nullptr) {
     const int win = (ex && ex->win) ? ex->win : WIN11;
     const BwdGeom g = bwd_geom(B, H, W, win);
     BwdParams p;
     memset(&p, 0, sizeof(p));
-    p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.gout = gout3; p.dF_unit = dF_unit;
+    p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.dF_unit = dF_unit;
+    p.gout[0] = up.g[0]; p.gout[1] = up.g[1]; p.gout[2] = up.g[2];
     p.B = B; p.H = H; p.W = W; p.Hout = g.Hout; p.Wout = g.Wout;
     p.seg_rows = g.seg_rows; p.nseg = g.nseg; p.nstrip = g.nstrip;
     make_taps(&p.taps, win, (ex && ex->win) ? ex->sigma : 1.5);
@@ -591,8 +596,9 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     if (!zmode && dF_unit) {
         const size_t n = (size_t)B * H * W;
         const int vec = (((uintptr_t)dF | (uintptr_t)dF_unit) & 15) == 0;
-        rescale_unit_kernel<<<148 * 8, 256, 0, st>>>(gout3, dF_unit, dF, n, vec);
+        rescale_unit_kernel<<<148 * 8, 256, 0, st>>>(up.g[0], up.g[1], up.g[2], dF_unit, dF, n, vec);
         MMIF_CUDA(cudaGetLastError());
+        count_launch(MMIF_CNT_RESCALE);
     }
     const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
                       cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
@@ -615,6 +621,7 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         else fusion_loss_bwd_kernel<11, false, false, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
     }
     MMIF_CUDA(cudaGetLastError());
+    count_launch(ex ? MMIF_CNT_SSIM_BWD_EXT : (zmode ? MMIF_CNT_LOSS_SINGLE_PASS : MMIF_CNT_LOSS_BWD));
     return MMIF_OK;
 }
 
@@ -630,7 +637,8 @@ extern "C" int mmif_fusion_loss_fwd(const float* i1, const float* i2, const floa
     if (cfg->want_grad) {
         if (!dF_unit) { set_error("want_grad needs dF_unit"); return MMIF_E_NULL; }
         if (((uintptr_t)dF_unit) & 3) { set_error("dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
-        return launch_bwd(i1, i2, f, B, H, W, cfg, nullptr, nullptr, dF_unit, true, out, ws, ws_bytes, (cudaStream_t)stream);
+        return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{nullptr, nullptr, nullptr}}, nullptr, dF_unit, true, out, ws, ws_bytes,
+                          (cudaStream_t)stream);
     }
     const size_t core = loss_ws_core_bytes(B, H, W);
     FwdLaunch L;
@@ -650,7 +658,27 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     if (rc) return rc;
     if (!gout3 || !dF) { set_error("null gout3/dF"); return MMIF_E_NULL; }
     if ((((uintptr_t)dF) | ((uintptr_t)dF_unit)) & 3) { set_error("dF / dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
-    return launch_bwd(i1, i2, f, B, H, W, cfg, gout3, dF_unit, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+    return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{gout3, gout3 + 1, gout3 + 2}}, dF_unit, dF, false, nullptr, ws, ws_bytes,
+                      (cudaStream_t)stream);
+}
+
+/* The same with the three upstream gradients as separate device scalars, as autograd hands them to the node
+ * (a NULL pointer = that loss value received no gradient = 0; at least one must be given). */
+extern "C" int mmif_fusion_loss_bwd3(const float* i1, const float* i2, const float* f, int B, int H, int W,
+                                     const MmifLossCfg* cfg, const float* g_ssim, const float* g_pixel, const float* g_grad,
+                                     const float* dF_unit, float* dF, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_common(i1, i2, f, B, H, W);
+    if (rc) return rc;
+    rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!dF) { set_error("null dF"); return MMIF_E_NULL; }
+    if (!g_ssim && !g_pixel && !g_grad) { set_error("no upstream gradient given"); return MMIF_E_NULL; }
+    if ((((uintptr_t)dF) | ((uintptr_t)dF_unit) | (uintptr_t)g_ssim | (uintptr_t)g_pixel | (uintptr_t)g_grad) & 3) {
+        set_error("dF / dF_unit / upstream gradients must be 4-byte aligned");
+        return MMIF_E_ALIGN;
+    }
+    return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{g_ssim, g_pixel, g_grad}}, dF_unit, dF, false, nullptr, ws, ws_bytes,
+                      (cudaStream_t)stream);
 }
 
 static double loss_sigma_of(int win) { return win == 11 ? 1.5 : 0.15 * (win - 1); }     // loss.py:34
@@ -687,7 +715,8 @@ extern "C" int mmif_ssim_bwd_ex_win(const float* i1, const float* i2, const floa
     memset(&ex, 0, sizeof(ex));
     ex.pair_w = pair_w; ex.ssim_base = scale; ex.cs_only = cs_only; ex.do_sobel = 0; ex.use_base = true;
     if (win != WIN11) { ex.win = win; ex.sigma = loss_sigma_of(win); }
-    return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
+    return launch_bwd(i1, i2, f, B, H, W, &cfg, Upstream{{gout1, nullptr, nullptr}}, nullptr, dF, false, nullptr, ws, ws_bytes,
+                      (cudaStream_t)stream, &ex);
 }
 
 /* calc_ssim(size_average=True) of the loss module for a window of 11, 9, 7, 5 or 3 taps (SSIM(win_size), loss.py:163-185;
@@ -777,5 +806,6 @@ extern "C" int mmif_mswssim_bwd(const float* i1, const float* i2, const float* f
     BwdExtra ex;
     memset(&ex, 0, sizeof(ex));
     ex.ssim_base = scale; ex.use_base = true; ex.win = win; ex.sigma = loss_sigma_of(win); ex.msw = 1; ex.accum = accumulate;
-    return launch_bwd(i1, i2, f, B, H, W, &cfg, gout1, nullptr, dF, false, nullptr, ws, ws_bytes, (cudaStream_t)stream, &ex);
+    return launch_bwd(i1, i2, f, B, H, W, &cfg, Upstream{{gout1, nullptr, nullptr}}, nullptr, dF, false, nullptr, ws, ws_bytes,
+                      (cudaStream_t)stream, &ex);
 }

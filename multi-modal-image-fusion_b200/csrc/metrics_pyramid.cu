@@ -82,6 +82,7 @@ static int run_ssim_level(const float* a, const float* b, const float* f, int N,
     if (small_need <= ws.fwd_ws_bytes) { part = (double*)(ws.fwd_ws + ws_counters_bytes(N)); cnt = (unsigned*)ws.fwd_ws; }
     ssim_small_kernel<<<grid, 256, 0, st>>>(a, b, f, H, W, k, taps, (0.01 * R) * (0.01 * R), (0.03 * R) * (0.03 * R), part, cnt,
                                             sums, stride);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -136,9 +137,11 @@ static int launch_halve(const Ptr3& p, int N, int H, int W, int Ho, int Wo, cuda
     if (vec) {
         dim3 grid(ceil_div(Wo, 64), ceil_div(Ho, 16), 3 * N);
         halve4_kernel<<<grid, 256, 0, st>>>(p, N, H, W, Ho, Wo);
+        mmif::count_launch(MMIF_CNT_METRIC);
     } else {
         dim3 grid(ceil_div(Wo, 64), ceil_div(Ho, 4), 3 * N);
         halve_kernel<<<grid, 256, 0, st>>>(p, N, H, W, Ho, Wo);
+        mmif::count_launch(MMIF_CNT_METRIC);
     }
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
@@ -199,6 +202,7 @@ static int launch_bd(const Ptr3& p, int N, int H, int W, int Ho, int Wo, const T
     const bool vec = ((W & 1) == 0) && ((((uintptr_t)p.src[0] | (uintptr_t)p.src[1] | (uintptr_t)p.src[2]) & 7) == 0);
     if (vec) blur_decimate_kernel<K, true><<<grid, 128, 0, st>>>(p, N, H, W, Ho, Wo, taps);
     else blur_decimate_kernel<K, false><<<grid, 128, 0, st>>>(p, N, H, W, Ho, Wo, taps);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -475,6 +479,7 @@ extern "C" int mmif_ssim(const float* a, const float* b, const float* f, int N, 
     rc = run_ssim_level(a, b, f, N, H, W, win_size, data_range, w.raw + RAW_SSIM, kRawPerPair, w, st); if (rc) return rc;
     const int k = win_size < H ? (win_size < W ? win_size : W) : (H < W ? H : W);
     ssim_out_kernel<<<ceil_div(N, 128), 128, 0, st>>>(w.raw + RAW_SSIM, kRawPerPair, N, 1.0 / ((double)(H - k + 1) * (W - k + 1)), out);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -488,6 +493,7 @@ extern "C" int mmif_msssim(const float* a, const float* b, const float* f, int N
     cudaStream_t st = (cudaStream_t)stream;
     rc = run_msssim(a, b, f, N, H, W, win_size, data_range, w.raw + RAW_MS, kRawPerPair, w, st); if (rc) return rc;
     msssim_out_kernel<<<ceil_div(N, 128), 128, 0, st>>>(w.raw + RAW_MS, kRawPerPair, N, msssim_dims(H, W, win_size), out);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -500,6 +506,7 @@ extern "C" int mmif_viff(const float* a, const float* b, const float* f, int N, 
     cudaStream_t st = (cudaStream_t)stream;
     rc = run_vif(a, b, f, N, H, W, w.raw + RAW_VIF, kRawPerPair, w, st); if (rc) return rc;
     viff_out_kernel<<<ceil_div(N, 128), 128, 0, st>>>(w.raw + RAW_VIF, kRawPerPair, N, out);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -565,6 +572,7 @@ extern "C" int mmif_eval_suite(const float* a, const float* b, const float* f, i
     if (rc_p) return rc_p;
     if (rc_h) return rc_h;
     suite_out_kernel<<<ceil_div(N, 128), 128, 0, st>>>(w.raw, N, msssim_dims(H, W, 11), 1.0 / ((double)(H - 10) * (W - 10)), out);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }

@@ -202,6 +202,7 @@ int launch_pixel_metrics(const float* a, const float* b, const float* f, int N, 
         pixel_metrics_kernel<true, false><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride);
     else
         pixel_metrics_kernel<false, true><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -404,6 +405,7 @@ int launch_hist(const float* a, const float* b, const float* f, int N, int H, in
     }
     dim3 grid(2 * S, N);
     hist_kernel<<<grid, kHT, sizeof(HistSmem), st>>>(a, b, f, P, S, counts, ws.hist_extra, ent, estride);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -439,6 +441,7 @@ int launch_tv(const float* x, int N, int H, int W, int norm, float weight, doubl
     const int rpb = stats_rows_per_block(N, H);
     dim3 grid(ceil_div(H, rpb), N);
     tv_kernel<<<grid, 256, 0, st>>>(x, H, W, rpb, norm, weight, (long long)N, ws.partial, ws.counters, out);
+    mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }

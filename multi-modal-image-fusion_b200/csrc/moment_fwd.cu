@@ -55,6 +55,8 @@ static int launch_t(const CUtensorMap& m1, const CUtensorMap& m2, const CUtensor
     }
     moment_fwd_kernel<WIN, EPI><<<grid, kNT, sizeof(SmemF), st>>>(m1, m2, my, p);
     MMIF_CUDA(cudaGetLastError());
+    count_launch((EPI == EPI_SSIM && WIN == 11 && p.do_sobel && p.fin.finalize == FIN_LOSS && !p.denorm) ? MMIF_CNT_LOSS_FWD
+                                                                                                         : MMIF_CNT_MOMENT_FWD);
     return MMIF_OK;
 }
 

@@ -33,8 +33,11 @@ struct FinishParams {
     double* partial;         // [B][nblk][8]
     double* sums;            // per-sample raw sums: sums[n*sums_stride + 0..7]
     long long sums_stride;
-    double* out;             // FIN_LOSS: loss block (mmif_b200.h MMIF_LOSS_*)
+    double* out;             // FIN_LOSS: loss block (mmif_b200.h MMIF_LOSS_*), followed by its float32 mirror
 };
+// float32 mirror of the loss block (same indices), stored right behind the doubles: what a float32 caller
+// (the autograd wrapper) reads without a conversion kernel.
+static inline size_t loss_block_doubles(int B) { return (size_t)MMIF_LOSS_HEAD + (size_t)(B > 0 ? B : 0) * MMIF_LOSS_PER_SAMPLE; }
 
 #ifdef __CUDACC__
 // v[] = this thread's 8 partial sums ([ssim1, ssim2, cs1, cs2, sig1, sig2, pix, grad] for the SSIM
@@ -73,6 +76,10 @@ __device__ __forceinline__ void cta_finish(const FinishParams& p, double (&v)[8]
             double* so = p.out + MMIF_LOSS_HEAD + (size_t)n * MMIF_LOSS_PER_SAMPLE;
             so[0] = t[0] * inv; so[1] = t[2] * inv; so[2] = t[4] * inv;   // ssim1, cs1, sigma1
             so[3] = t[1] * inv; so[4] = t[3] * inv; so[5] = t[5] * inv;   // ssim2, cs2, sigma2
+            float* out32 = reinterpret_cast<float*>(p.out + (size_t)MMIF_LOSS_HEAD + (size_t)p.B * MMIF_LOSS_PER_SAMPLE);
+            float* so32 = out32 + MMIF_LOSS_HEAD + (size_t)n * MMIF_LOSS_PER_SAMPLE;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) so32[i] = (float)so[i];
             __threadfence();
             const unsigned prev = atomicAdd(&p.counters[p.B], 1u);
             if (prev == (unsigned)(p.B - 1)) {
@@ -90,6 +97,10 @@ __device__ __forceinline__ void cta_finish(const FinishParams& p, double (&v)[8]
                 p.out[MMIF_LOSS_PIXEL] = l_pix;
                 p.out[MMIF_LOSS_GRAD] = l_grad;
                 p.out[MMIF_LOSS_TOTAL] = l_ssim + l_pix + l_grad;
+                out32[MMIF_LOSS_SSIM] = (float)l_ssim;
+                out32[MMIF_LOSS_PIXEL] = (float)l_pix;
+                out32[MMIF_LOSS_GRAD] = (float)l_grad;
+                out32[MMIF_LOSS_TOTAL] = (float)(l_ssim + l_pix + l_grad);
                 p.counters[p.B] = 0u;
             }
         }

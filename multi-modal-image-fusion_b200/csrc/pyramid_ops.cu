@@ -156,6 +156,7 @@ extern "C" int mmif_halve(const float* src, int N, int H, int W, float* dst, voi
     int rc = chk(src, dst, N, H, W); if (rc) return rc;
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     halve1_kernel<<<dim3(ceil_div(Wo, 64), ceil_div(Ho, 4), N), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, Ho, Wo);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -163,6 +164,7 @@ extern "C" int mmif_halve_bwd(const float* g_dst, int N, int H, int W, float* g_
     int rc = chk(g_dst, g_src_accum, N, H, W); if (rc) return rc;
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     halve1_bwd_kernel<<<dim3(ceil_div(W, 64), ceil_div(H, 4), N), 256, 0, (cudaStream_t)stream>>>(g_dst, g_src_accum, H, W, Ho, Wo);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -170,6 +172,7 @@ extern "C" int mmif_reflect_pad(const float* src, int N, int H, int W, int pad, 
     int rc = chk(src, dst, N, H, W); if (rc) return rc;
     if (pad < 0 || pad >= H || pad >= W) { set_error("reflect pad %d must be smaller than H, W", pad); return MMIF_E_SHAPE; }
     reflect_pad_kernel<<<dim3(ceil_div(W + 2 * pad, 64), ceil_div(H + 2 * pad, 4), N), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, pad);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -177,6 +180,7 @@ extern "C" int mmif_reflect_pad_bwd(const float* g_dst, int N, int H, int W, int
     int rc = chk(g_dst, g_src, N, H, W); if (rc) return rc;
     if (pad < 0 || pad >= H || pad >= W) { set_error("reflect pad %d must be smaller than H, W", pad); return MMIF_E_SHAPE; }
     reflect_pad_bwd_kernel<<<dim3(ceil_div(W, 64), ceil_div(H, 4), N), 256, 0, (cudaStream_t)stream>>>(g_dst, g_src, H, W, pad);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -187,6 +191,7 @@ extern "C" int mmif_tv_loss_bwd(const float* x, int N, int H, int W, int norm, f
     if (norm != MMIF_NORM_L1 && norm != MMIF_NORM_L2) { set_error("unsupported norm"); return MMIF_E_MODE; }
     const float kv = weight / ((float)N * (float)(H - 1) * (float)W), kh = weight / ((float)N * (float)H * (float)(W - 1));
     tv_bwd_kernel<<<dim3(ceil_div(W, 64), ceil_div(H, 4), N), 256, 0, (cudaStream_t)stream>>>(x, gout1, gx, H, W, norm, kv, kh);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -199,6 +204,7 @@ extern "C" int mmif_widen_u8(const unsigned char* src, size_t n, float* dst, voi
     size_t blocks = (n / 16 + 255) / 256;
     blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
     widen_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n, vec);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -212,6 +218,7 @@ extern "C" int mmif_norm_loss(const float* x, size_t n, int norm, float weight, 
     blocks = blocks < 1 ? 1 : (blocks > (size_t)kNormBlocks ? (size_t)kNormBlocks : blocks);
     norm_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, norm, (double)weight / (double)n, (unsigned*)ws,
                                                                           (double*)((unsigned char*)ws + 256), out);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }
@@ -222,6 +229,7 @@ extern "C" int mmif_norm_loss_bwd(const float* x, size_t n, int norm, float weig
     size_t blocks = (n + 1023) / 1024;
     blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
     norm_loss_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, norm, weight / (float)n, gout1, gx);
+    mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
 }

@@ -54,7 +54,14 @@ def test_argument_validation_without_gpu():
     assert lib.mmif_fusion_loss_fwd(16, 16, 16, 1, 32, 32, ctypes.byref(bad), 16, None, 16, 0, None) == -3   # mode
     assert lib.mmif_loss_workspace_bytes(1, 8, 8) == 0
     assert lib.mmif_loss_workspace_bytes(64, 3072, 4096) > 0
-    assert lib.mmif_loss_out_doubles(3) == 4 + 18
+    assert lib.mmif_loss_out_doubles(3) == (4 + 18) + (4 + 18 + 1) // 2          # the double block + its float32 mirror
+    g = ctypes.c_float(1.0)
+    assert lib.mmif_fusion_loss_bwd3(16, 16, 16, 1, 32, 32, ctypes.byref(cfg), None, None, None, None, 16, 16, 0, None) == -1   # no upstream
+    assert lib.mmif_fusion_loss_bwd3(16, 16, 16, 1, 32, 32, ctypes.byref(cfg), 18, None, None, None, 16, 16, 0, None) == -5    # alignment
+    assert lib.mmif_fusion_loss_bwd3(16, 16, 16, 1, 32, 32, ctypes.byref(cfg), 16, None, None, None, None, 16, 0, None) == -1   # null dF
+    counts = (ctypes.c_ulonglong * 16)()
+    assert lib.mmif_launch_counts(counts, 16) == 0 and lib.mmif_launch_counts(None, 16) == -1
+    assert L.launch_counts()['loss_single_pass'] == 0          # nothing has been launched on this GPU-less host
     assert lib.mmif_metric_workspace_bytes(21, 480, 640) > 21 * (3 * 256 + 2 * 65536) * 4
     assert lib.mmif_set_gaussian_taps(18, 1.5, (ctypes.c_float * 18)()) == -2
     # SSIM(win_size) entries: window set, shape against the window, null pointers, workspace

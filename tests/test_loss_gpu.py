@@ -74,11 +74,16 @@ def test_loss_backward_vs_fp64_oracle(name):
     scale_ratio = np.abs(ref[0]).max() / np.abs(tot64).max()
     assert mx <= max(gates.RTOL, ref32_err / max(scale_ratio, 1e-30)), \
         f'{name}: ssim grad max-norm err {mx:.3e} at {where} (fp32 reference: {ref32_err:.3e})'
-    for k, nm in ((1, 'pixel'), (2, 'grad')):
-        frac, mx, where = gates.grad_report(grads[k], ref[k])
-        if name in cases.LOSS_GRAD_TIE_CASES:
-            continue   # exact ties: sign(0) of a value that is exactly / nearly 0
-        assert frac <= 1e-4, f'{name}: {nm} grad: {frac:.2e} of elements differ, max {mx:.3e} at {where}'
+    # L1 terms: every element is held to 1e-5 max|g| except those a NEAR tie of a sign() argument can flip (masked and
+    # counted); an EXACT tie (sign(0) = 0) is asserted, not skipped: with imgf == max(img1, img2) the pixel
+    # gradient is exactly zero everywhere.
+    a64, b64, f64 = cases.loss_case(name)
+    pix_mask, sob_mask, pix_zero = gates.l1_tie_masks(a64, b64, f64)
+    for k, nm, mask in ((1, 'pixel', pix_mask), (2, 'grad', sob_mask)):
+        frac, mx, masked = gates.masked_grad_report(grads[k], ref[k], mask)
+        assert frac <= 1e-4, f'{name}: {nm} grad: {frac:.2e} of the untied elements differ, max {mx:.3e} ({masked:.2e} masked as ties)'
+        assert masked <= (0.10 if name in cases.LOSS_GRAD_TIE_CASES else 1e-3), f'{name}: {nm}: {masked:.2e} of the elements are ties'
+    assert np.all(grads[1][pix_zero] == 0.0), f'{name}: pixel gradient must be exactly 0 where imgf == max(img1, img2)'
 
 
 def test_total_backward_and_memo_single_node():
@@ -99,8 +104,6 @@ def test_total_backward_and_memo_single_node():
 def test_secondary_modes(pixel):
     a, b, f = (T(x) for x in cases.loss_case('rand_2x40x37'))
     vals, grads = run_new(a, b, f, True, pixel=pixel, grad=pixel)
-    for dt, store in ((torch.float32, 'r32'), (torch.float64, 'r64')):
-        pass
     r32 = [OL.pixel_loss(a, b, f, pixel[0], 0.01, pixel[1]).item(), OL.grad_loss(a, b, f, pixel[0], 0.1, pixel[1]).item()]
     ad, bd = a.double(), b.double()
     fd = f.double().requires_grad_(True)
@@ -112,7 +115,7 @@ def test_secondary_modes(pixel):
     gates.assert_scalar('grad', vals[2], r32[1], g64.item())
     for got, ref, nm in ((grads[1], gp.numpy(), 'pixel'), (grads[2], gg.numpy(), 'grad')):
         frac, mx, where = gates.grad_report(got, ref)
-        assert frac <= 1e-3, f'{nm} {pixel}: {frac:.2e} differ, max {mx:.3e} at {where}'
+        assert frac <= 1e-4, f'{nm} {pixel}: {frac:.2e} differ, max {mx:.3e} at {where}'
 
 
 def test_errors_match_reference():
