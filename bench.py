@@ -115,20 +115,41 @@ def physical_gpu_index(local):
 
 
 # ------------------------------------------------------------------------------------ reference arm
+def reference_objective():
+    """-> (fn(a, b, f) running loss fwd+bwd on the host and returning the gradient, kind, description).
+    kind "reference": the reference's OWN core/loss.py modules (byte-compiled artefact oracle/_ref, built by
+    oracle/build_ref.py where /root/reference exists); kind "port": the oracle restatement (bit-pinned to it)."""
+    try:
+        from oracle import build_ref
+        RL, _, _ = build_ref.load()
+        f1, f2, f3 = RL.SSIMLoss('ssim', weight=1.0), RL.PixelLoss('l1', weight=0.01), RL.GradLoss('l1', weight=0.1)   # train.py:302-308
+
+        def run(a, b, f):
+            y = f.detach().requires_grad_(True)
+            (f1(a, b, y) + f2(a, b, y, mode='max') + f3(a, b, y, mode='max')).backward()       # train.py:64-71
+            return y.grad
+        return run, 'reference', "cpu torch, the reference's own core/loss.py (oracle/_ref)"
+    except ImportError:
+        from oracle import fusion_loss as OL
+
+        def run(a, b, f):
+            return OL.train_objective_grad(a, b, f)[1]
+        return run, 'port', 'cpu torch, oracle port of core/loss.py (oracle/_ref not built)'
+
+
 def run_reference(args, rank):
-    """The reference's own CPU implementation of the path (oracle/ = op-for-op restatement of
-    core/loss.py; /root/reference is not on the GPU box), all host threads, one bounded sample per
+    """The reference's own CPU implementation of the path, all host threads, one bounded sample per
     step: loss fwd+bwd on ONE 4096x3072 pair of the same workload."""
     if rank != 0:
         return
-    from oracle import fusion_loss as OL
+    run, kind, host = reference_objective()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     a, b, f = (torch.rand(1, 1, H, W, generator=g) for _ in range(3))
 
     def step():
-        OL.train_objective_grad(a, b, f)
+        run(a, b, f)
 
     nwarm = min(args.warmup, 3)            # each step is ~4.5 s of host time on the GPU box
     for _ in range(nwarm):
@@ -143,8 +164,8 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': nwarm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': sample, 'host': 'cpu torch, oracle port of core/loss.py'},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+        'config': {'workload': WORKLOAD, 'sample': sample, 'host': host},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -173,23 +194,37 @@ def main():
 
     if GLOBAL_B % world:
         raise SystemExit(f'global batch {GLOBAL_B} not divisible by {world} ranks')
+    from mmif_b200 import dist_utils as DU
     B = GLOBAL_B // world
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     a, b, f = (torch.rand(B, 1, H, W, device=dev, generator=g) for _ in range(3))
     lib = L.load()
     L.ensure_device(dev)
-    cfg = ML._cfg(1.0, 'max', 'max', 'l1', 'l1')
-    cfg.w_ssim, cfg.w_pixel, cfg.w_grad = 1.0, 0.01, 0.1             # train.py:302-308
+    # ---- the timed step IS the reference's call sequence (train.py:64-71) on the drop-in modules -------------------
+    fn1, fn2, fn3 = ML.SSIMLoss('ssim', weight=1.0), ML.PixelLoss('l1', weight=0.01), ML.GradLoss('l1', weight=0.1)   # train.py:302-308
+
+    def step(ev=None):
+        y = f.detach().requires_grad_(True)              # a fresh imgf every step, as the network produces one
+        if ev:
+            ev[0].record()
+        l1 = fn1(a, b, y)                                # launches fusion_loss_bwd_kernel<11,1,1,0>: loss values + d(total)/d imgf
+        if ev:
+            ev[1].record()
+        total = l1 + fn2(a, b, y, mode='max') + fn3(a, b, y, mode='max')      # the other two read the same launch
+        total.backward()                                 # rescale_unit_kernel: in place, exits at once for unit upstream
+        if ev:
+            ev[2].record()
+        if world > 1:                                    # the path's only collective: ONE 16-byte all-reduce, in place on the
+            DU.reduce_loss_vector(ML.last_loss_vector(), world)      # kernel's own output vector (train.py:92-96 does four)
+        return y.grad
+
+    # ---- the same work straight through the C ABI: two-kernel path (forward, then recomputing backward) --------------
+    cfg = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
     out = torch.empty(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device=dev)
     ws = torch.zeros(lib.mmif_loss_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
     gout = torch.ones(3, device=dev)
     dF = torch.empty_like(f)
-    red = torch.zeros(4, device=dev)
     st = L.stream_ptr(dev)
-
-    cfg_z = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
-    cfg_z.want_grad = 1
-    dU = torch.empty_like(f)
 
     def fwd():        # two-kernel path, kernel 1: loss values only (12 B/px)
         L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg),
@@ -199,34 +234,19 @@ def main():
         L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg),
                                          gout.data_ptr(), None, dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
 
-    def zfwd():       # single-pass path (what the drop-in modules run): loss values + d(total)/dIf in ONE launch (16 B/px)
-        L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg_z),
-                                         out.data_ptr(), dU.data_ptr(), ws.data_ptr(), ws.numel(), st))
-
-    def zbwd():       # its backward, as the drop-in modules call it: in place on dU; the upstream gradients are equal and 1
-                      # (total.backward()), so the two launches decide that on the device and exit
-        L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg_z),
-                                         gout.data_ptr(), dU.data_ptr(), dU.data_ptr(), ws.data_ptr(), ws.numel(), st))
-
-    def reduce_scalars():
-        if world > 1:           # the path's only collective: ONE 16-byte all-reduce (train.py:92-96 does four)
-            red.copy_(out[:4])
-            dist.all_reduce(red)
-            red.div_(world)
-
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(first, second, steps):
+    def timed(run, steps):
+        """run(ev) records ev[0..2] around its two phases; returns (ms per step = max over ranks, mean ms of each phase)."""
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
         t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
         t_begin.record()
         for k in range(steps):
-            ev[k][0].record(); first(); ev[k][1].record(); second(); ev[k][2].record()
-            reduce_scalars()
+            run(ev[k])
         t_end.record()
         sync_all()
         ms_total = t_begin.elapsed_time(t_end)
@@ -237,37 +257,59 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         return tmax.item() / steps, ms_a, ms_b
 
+    def two_kernel_step(ev):
+        ev[0].record(); fwd(); ev[1].record(); bwd(); ev[2].record()
+
     for _ in range(max(args.warmup, 3)):
-        zfwd(); zbwd(); reduce_scalars()
+        step()
     sync_all()
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
-    ms_step, ms_z, ms_rescale = timed(zfwd, zbwd, args.steps)
+    c0 = L.launch_counts()
+    ms_step, ms_z, ms_rest = timed(step, args.steps)
+    c1 = L.launch_counts()
     clocks = sampler.stop()
+    launches = {k: c1[k] - c0[k] for k in c1}
+    assert launches['loss_single_pass'] == args.steps and launches['loss_fwd'] == 0 and launches['loss_bwd'] == 0, launches
+    grad_modules = step()
+    vec = ML.last_loss_vector().double().cpu()
     for _ in range(3):
         fwd(); bwd()
-    ms_step2, ms_fwd, ms_bwd = timed(fwd, bwd, args.steps)
+    ms_step2, ms_fwd, ms_bwd = timed(two_kernel_step, args.steps)
     total_mpix = GLOBAL_B * H * W / 1e6
     value = total_mpix / (ms_step * 1e-3)
+
+    # ---- output checks on the timed path (a fast kernel with wrong results is not done) -----------------------------------
+    torch.cuda.synchronize()
+    ref_blk = out[:4].cpu()
+    gscale = dF.abs().max().item()
+    checks = {'single_pass_vs_two_kernel_grad_maxnorm': (grad_modules - dF).abs().max().item() / gscale,
+              'single_pass_vs_two_kernel_loss_rel': max(abs(vec[k].item() - ref_blk[k].item()) / abs(ref_blk[k].item()) for k in range(3))
+              if world == 1 else None}
+    assert checks['single_pass_vs_two_kernel_grad_maxnorm'] <= 2e-6, checks
+    del grad_modules
+    if rank == 0:
+        checks.update(crop_parity_check(dev, ML, a, b, f))
 
     # ---- roofline of the dominant kernel (single-pass loss+gradient: 16 algorithmic bytes per pixel) ----
     peak, peak_src = measured_peak()
     local_pix = B * H * W
     gbs = lambda bpp, ms: bpp * local_pix / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             tj = json.load(fh)
-        traffic = tj['fusion_loss_bwd_kernel<FAST,ZMODE>']['dram_bytes_per_pixel'] * local_pix
+        ent = tj['fusion_loss_bwd_kernel<FAST,ZMODE>']
+        traffic = ent['dram_bytes_per_pixel'] * local_pix
+        traffic_src = 'stored constant: ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel (%s), per pixel x the pixels of one launch; not measured in this run' % ent.get('capture', 'profiles/traffic.json')
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_bwd_kernel<FAST=1,ZMODE=1> (loss values + dIf, one launch)',
+    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_bwd_kernel<11, FAST=1, ZMODE=1, EXT=0> (loss values + dIf, one launch) as launched by core.loss.SSIMLoss',
                 'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
-                'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
                 'ms_per_launch': ms_z,
-                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4, profiles/r1f_zkernel.txt: FMA pipe 66% active, '
-                        'DRAM 9.8%, traffic 17.0 B/px): 264 FMA/px of exact-fp32 separable blurs alone cap the kernel at 27% of the HBM roof; '
-                        'see roofline_fp32 for the roof that binds'}
+                'note': 'FP32-FMA-pipe bound, not HBM bound (DESIGN.md section 4): 264 FMA/px of exact-fp32 separable blurs alone cap the '
+                        'kernel at 27% of the HBM roof; see roofline_fp32 for the roof that binds'}
     # secondary roof, the one that binds: ALGORITHMIC fp32 FMAs (12 blurred maps x 2 passes x 11 taps = 264 FMA/px, the
     # irreducible part; epilogue / Sobel / products excluded) against the measured packed-FMA issue rate of B200
     # (tools/microbench/pipes.cu, profiles/pipes_r1.txt: 58.4 FFMA2/clk/SM = 116.8 FMA/clk/SM at 1965 MHz x 148 SMs)
@@ -281,18 +323,21 @@ def main():
                   'bwd': {'kernel': 'fusion_loss_bwd_kernel<FAST=1,ZMODE=0>', 'ms_per_launch': ms_bwd, 'achieved': gbs(ALG_BYTES_BWD, ms_bwd),
                           'frac': gbs(ALG_BYTES_BWD, ms_bwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD},
                   'combined_28B': {'achieved': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd),
-                                   'frac': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd) / peak}}
+                                   'frac': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd) / peak},
+                  'note': 'C-ABI calls (mmif_fusion_loss_fwd without want_grad, then mmif_fusion_loss_bwd): what backward costs when the '
+                          'upstream gradients differ or a graph is retained; not the path the timed step takes'}
 
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'per_rank_batch': B, 'parallelism': f'batch sharded over {world} rank(s)',
-                   'path': 'single-pass (loss + gradient in one launch; backward rescales that buffer in place, a no-op for unit upstream); two_kernel = fwd then recomputing bwd',
+                   'path': 'core.loss.SSIMLoss + PixelLoss + GradLoss on device-resident tensors, total.backward() (train.py:64-71): '
+                           'ONE single-pass launch (loss + gradient) + the in-place rescale; launch counters asserted in-run',
                    'l2': 'inputs larger than L2 (per-rank tensors %.0f MB each)' % (B * H * W * 4 / 1e6),
-                   'collective': 'one 16-byte all-reduce of the loss scalars per step' if world > 1 else 'none'},
-        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'backward_ms': ms_rescale, 'two_kernel': two_kernel, 'clocks': clocks,
-        'gpu_launches': 3 * args.steps,
+                   'collective': 'one 16-byte all-reduce (AVG) in place on the kernel\'s loss vector per step' if world > 1 else 'none'},
+        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'ms_after_kernel': ms_rest, 'two_kernel': two_kernel, 'clocks': clocks,
+        'checks': checks, 'gpu_launches': L.kernel_launches(c0, c1), 'launch_counts': launches,
     }
 
     if not args.no_extras:
@@ -316,61 +361,99 @@ def main():
         dist.destroy_process_group()
 
 
+def crop_parity_check(dev, ML, a, b, f):
+    """Parity of the timed path on a crop of the timed tensors: sample 0, rows/cols 0..383 x 0..511 of the bench inputs
+    through the same modules, against the fp64 oracle on the host (gates of tests/gates.py)."""
+    from oracle import fusion_loss as OL
+    ca, cb, cf = (t[:1, :, :384, :512].contiguous() for t in (a, b, f))
+    y = cf.clone().requires_grad_(True)
+    l1 = ML.SSIMLoss('ssim', weight=1.0)(ca, cb, y)
+    l2 = ML.PixelLoss('l1', weight=0.01)(ca, cb, y, mode='max')
+    l3 = ML.GradLoss('l1', weight=0.1)(ca, cb, y, mode='max')
+    (l1 + l2 + l3).backward()
+    (r1, r2, r3), g64 = OL.train_objective_grad(ca.cpu().double(), cb.cpu().double(), cf.cpu().double())
+    rel = [abs(x.item() - r.item()) / abs(r.item()) for x, r in zip((l1, l2, l3), (r1, r2, r3))]
+    diff = (y.grad.cpu().double() - g64).abs() / g64.abs().max().item()
+    frac = (diff > 1e-5).double().mean().item()          # L1 sign ties (SURVEY 8(c)) are counted, not hidden: <= 1e-4 of the elements
+    assert max(rel) <= 1e-5 and frac <= 1e-4, (rel, frac)
+    return {'crop_1x384x512_loss_rel_vs_fp64_oracle': max(rel), 'crop_1x384x512_grad_frac_beyond_1e-5_vs_fp64_oracle': frac,
+            'crop_1x384x512_grad_median_rel_err': diff.median().item()}
+
+
 def e2e_leg(args, dev, world, rank, ML, B):
-    """Same metric through the public drop-in modules with HOST buffers: every step copies the
-    rank's shard of I1/I2/If from pinned host memory (chunked, double-buffered against the
-    compute), runs SSIMLoss+PixelLoss+GradLoss forward and backward, and reads the loss back."""
+    """Same metric through the public drop-in modules with HOST buffers, as a training step sees them (train.py:57-71):
+    every step copies the rank's shard of the SOURCES I1 / I2 from pinned host memory (chunked, double-buffered against
+    the compute) — float32 as the reference's DataLoader delivers them, and, second figure, uint8 widened to
+    float32 / 255 on the device (core.loss.ingest_u8, bit-identical to the host-side scaling) — while imgf is where
+    train.py:63 leaves it, on the device (it is the network's output); runs SSIMLoss + PixelLoss + GradLoss forward and
+    backward per chunk and reads the loss back."""
     import torch.distributed as dist
     chunk = 8 if B % 8 == 0 else B
     nchunk = B // chunk
     steps = max(1, min(args.steps, 3))
-    host = [torch.empty(B, 1, H, W, pin_memory=True) for _ in range(3)]
-    for t in host:
-        t.uniform_(0, 1)
-    dbuf = [[torch.empty(chunk, 1, H, W, device=dev) for _ in range(3)] for _ in range(2)]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    imgf = torch.rand(B, 1, H, W, device=dev, generator=g)
+    fn1, fn2, fn3 = ML.SSIMLoss('ssim', weight=1.0), ML.PixelLoss('l1', weight=0.01), ML.GradLoss('l1', weight=0.1)
     copy_stream = torch.cuda.Stream(device=dev)
     comp = torch.cuda.current_stream(dev)
-    fn1, fn2, fn3 = ML.SSIMLoss('ssim', weight=1.0), ML.PixelLoss('l1', weight=0.01), ML.GradLoss('l1', weight=0.1)
     loss_host = torch.empty(1, pin_memory=True)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
+    out = {}
+    for tag, dtype in (('f32', torch.float32), ('u8', torch.uint8)):
+        host = [torch.empty(B, 1, H, W, dtype=dtype, pin_memory=True) for _ in range(2)]
+        for t in host:
+            if dtype == torch.uint8:
+                t.random_(0, 256)
+            else:
+                t.uniform_(0, 1)
+        stage = [[torch.empty(chunk, 1, H, W, dtype=dtype, device=dev) for _ in range(2)] for _ in range(2)]
+        wide = [[torch.empty(chunk, 1, H, W, device=dev) for _ in range(2)] for _ in range(2)] if dtype == torch.uint8 else stage
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
 
-    def step():
-        acc = torch.zeros((), device=dev)
-        for c in range(nchunk):
-            s = c & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[s])
-                for k in range(3):
-                    dbuf[s][k].copy_(host[k][c * chunk:(c + 1) * chunk], non_blocking=True)
-                ready[s].record(copy_stream)
-            comp.wait_event(ready[s])
-            x1, x2 = dbuf[s][0], dbuf[s][1]
-            y = dbuf[s][2].detach().requires_grad_(True)
-            tot = (fn1(x1, x2, y) + fn2(x1, x2, y, mode='max') + fn3(x1, x2, y, mode='max')) / nchunk
-            tot.backward()
-            acc = acc + tot.detach()
-            free[s].record(comp)
-        loss_host.copy_(acc.reshape(1), non_blocking=True)
-        torch.cuda.synchronize()
-        return loss_host.item()
+        def step():
+            acc = torch.zeros((), device=dev)
+            for c in range(nchunk):
+                s = c & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[s])
+                    for k in range(2):
+                        stage[s][k].copy_(host[k][c * chunk:(c + 1) * chunk], non_blocking=True)
+                    ready[s].record(copy_stream)
+                comp.wait_event(ready[s])
+                if dtype == torch.uint8:
+                    for k in range(2):
+                        ML.ingest_u8(stage[s][k], out=wide[s][k])
+                x1, x2 = wide[s][0], wide[s][1]
+                y = imgf[c * chunk:(c + 1) * chunk].detach().requires_grad_(True)
+                tot = (fn1(x1, x2, y) + fn2(x1, x2, y, mode='max') + fn3(x1, x2, y, mode='max')) / nchunk
+                tot.backward()
+                acc = acc + tot.detach()
+                free[s].record(comp)
+            loss_host.copy_(acc.reshape(1), non_blocking=True)
+            torch.cuda.synchronize()
+            return loss_host.item()
 
-    for s in range(2):
-        free[s].record(comp)
-    step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+        for s_ in range(2):
+            free[s_].record(comp)
         step()
-    torch.cuda.synchronize()
-    dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    return {'value': GLOBAL_B * H * W / 1e6 / dt.item(), 'unit': UNIT, 'h2d_bytes_per_step': 3 * GLOBAL_B * H * W * 4,
-            'd2h_bytes_per_step': 4 * world, 'steps': steps, 'gpu_launches_per_step': 2 * nchunk * world,
-            'api': 'core.loss.SSIMLoss/PixelLoss/GradLoss + backward, pinned host -> device per step (chunks of %d)' % chunk}
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[tag] = (GLOBAL_B * H * W / 1e6 / dt.item(), 2 * GLOBAL_B * H * W * host[0].element_size())
+        del host, stage, wide
+    return {'value': out['f32'][0], 'unit': UNIT, 'h2d_bytes_per_step': out['f32'][1], 'd2h_bytes_per_step': 4 * world, 'steps': steps,
+            'gpu_launches_per_step': 2 * nchunk * world,
+            'api': 'core.loss.SSIMLoss/PixelLoss/GradLoss + backward; sources I1, I2 float32 from pinned host memory every step (chunks of %d), '
+                   'imgf device-resident as train.py:63 produces it' % chunk,
+            'u8_sources': {'value': out['u8'][0], 'unit': UNIT, 'h2d_bytes_per_step': out['u8'][1],
+                           'api': 'the same with 8-bit sources widened to float32 / 255 on the device (core.loss.ingest_u8)'}}
 
 
 # ------------------------------------------------------------------------ library baselines (torch CUDA eager)
@@ -499,7 +582,13 @@ def train_step_leg(dev, world, rank, ML):
     drop-in loss modules; plus the loss-only (forward + backward to imgf) time of each.  Max over ranks."""
     import torch.distributed as dist
     torch.manual_seed(0)
-    net = _FusionNetStandIn().to(dev)
+    try:            # the reference's own DenseFuse (core/model.py:165-187) from the byte-compiled artefact oracle/_ref
+        from oracle import build_ref
+        net = build_ref.load()[2].DenseFuse().to(dev)
+        net_name = "the reference's DenseFuse (core/model.py:165-187, oracle/_ref)"
+    except ImportError:
+        net = _FusionNetStandIn().to(dev)
+        net_name = 'DenseFuse-shaped stand-in network (oracle/_ref not built)'
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index]) if world > 1 else net
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
@@ -537,8 +626,8 @@ def train_step_leg(dev, world, rank, ML):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         res[key] = ms.item()
-    res['config'] = 'DenseFuse-shaped stand-in network, per-rank batch 8 x 256x256 (global %d), Adam, clip 5, %s' % (
-        8 * world, 'DDP over NCCL' if world > 1 else 'single process')
+    res['config'] = '%s, per-rank batch 8 x 256x256 (global %d), Adam 1e-4, clip 5 (train.py:64-71), %s' % (
+        net_name, 8 * world, 'DDP over NCCL' if world > 1 else 'single process')
     res['global_mpix_per_step'] = 8 * world * 65536 / 1e6
     return res
 
@@ -627,6 +716,7 @@ def metric_suite_leg(dev, MM):
             return e0.elapsed_time(e1) / iters
 
         ms = timeit(lambda: MM.eval_metrics_batch(a, b, f), 10)
+        ms_sub = timeit(lambda: MM.eval_subset_batch(a, b, f), 10) if name.startswith('polar') else None
         # value-distribution check: uniform noise is the best case for the shared-memory histogram
         # atomics and the SSIM/VIF branches; smooth 8-bit fields with exactly flat patches are the worst
         import torch.nn.functional as F
@@ -679,23 +769,38 @@ def metric_suite_leg(dev, MM):
                      'eval_py_call_pattern_ms_per_pair': per_pair_ms,
                      'cpu_reference_pairs_per_s': 1.0 / cpu_s, 'cpu_cores': torch.get_num_threads(),
                      'cpu_sample': '1 pair, oracle port of eval.py:29-75, single run'}
+        if ms_sub is not None:      # BASELINE configs[3]: MS-SSIM + VIFF + Qabf only (51.6 algorithmic B/px)
+            out[name]['configs3_subset_msssim_viff_qabf'] = {
+                'pairs_per_s': n / (ms_sub * 1e-3), 'ms_per_batch': ms_sub,
+                'hbm_frac_51.6B_per_pixel': 51.6 * n * h * w / (ms_sub * 1e-3) / 1e9 / peak}
     return out
 
 
 def cpu_baseline_leg():
-    from oracle import fusion_loss as OL
+    """The reference's CPU path on the host cores (rank 0, N = 1): a bounded sample of the workload (one 4096x3072 pair)
+    and BASELINE configs[0] as named (one 1224x1024 pair, batch 1, CPU torch: SURVEY 8(d) C1, best of 5 after 1 warm-up)."""
+    run, kind, host = reference_objective()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     a, b, f = (torch.rand(1, 1, H, W, generator=g) for _ in range(3))
-    OL.train_objective_grad(a, b, f)
+    run(a, b, f)
     best = 1e30
     for _ in range(3):
         t0 = time.perf_counter()
-        OL.train_objective_grad(a, b, f)
+        run(a, b, f)
         best = min(best, time.perf_counter() - t0)
-    return {'value': H * W / 1e6 / best, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '1 of 64 pairs (one 4096x3072 pair, fwd+bwd), best of 3 after 1 warm-up'}
+    a, b, f = (torch.rand(1, 1, 1024, 1224, generator=g) for _ in range(3))
+    run(a, b, f)
+    best0 = 1e30
+    for _ in range(5):
+        t0 = time.perf_counter()
+        run(a, b, f)
+        best0 = min(best0, time.perf_counter() - t0)
+    return {'value': H * W / 1e6 / best, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind, 'host': host,
+            'sample': '1 of 64 pairs (one 4096x3072 pair, fwd+bwd), best of 3 after 1 warm-up',
+            'configs0_1x1024x1224': {'ms': best0 * 1e3, 'mpix_per_s': 1024 * 1224 / 1e6 / best0,
+                                     'sample': 'BASELINE configs[0]: one 1224x1024 pair, batch 1, loss fwd+bwd, best of 5 after 1 warm-up'}}
 
 
 if __name__ == '__main__':

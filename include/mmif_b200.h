@@ -272,6 +272,9 @@ int mmif_eval_suite_host(const float* a_host, const float* b_host, const float* 
  * the widening is exact).  dev_scratch: 3*N*H*W floats (device).  The _host form copies from host memory into
  * dev_u8 (3 * roundup16(N*H*W) bytes, device), runs the suite, copies the rows back and synchronises `stream`. */
 int mmif_widen_u8(const unsigned char* src, size_t n, float* dst, void* stream);
+/* dst[i] = float32(src[i]) / 255 in IEEE float32 division: the `uint8 / 255` scaling the reference's datasets apply on the host
+ * (data/dataset.py via torchvision to_tensor) done on the device, bit-identical, so training sources can be shipped as bytes. */
+int mmif_widen_u8_unit(const unsigned char* src, size_t n, float* dst, void* stream);
 int mmif_eval_suite_u8(const unsigned char* a, const unsigned char* b, const unsigned char* f, int N, int H, int W,
                        double* out, float* dev_scratch, void* ws, size_t ws_bytes, void* stream);
 int mmif_eval_suite_u8_host(const unsigned char* a_host, const unsigned char* b_host, const unsigned char* f_host,

@@ -16,7 +16,7 @@ SYMBOLS = [
     'mmif_fusion_loss_bwd3', 'mmif_launch_counts',
     'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_ssim_fwd_win', 'mmif_ssim_bwd_ex_win', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
     'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_ssim',
-    'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8',
+    'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8', 'mmif_widen_u8_unit',
     'mmif_eval_suite_u8', 'mmif_eval_suite_u8_host', 'mmif_norm_workspace_bytes', 'mmif_norm_loss', 'mmif_norm_loss_bwd', 'mmif_test_post',
 ]
 
@@ -87,6 +87,7 @@ def load():
     lib.mmif_ssim_maps.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.mmif_test_post.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, vp, sz, vp]
     lib.mmif_widen_u8.argtypes = [vp, sz, vp, vp]
+    lib.mmif_widen_u8_unit.argtypes = [vp, sz, vp, vp]
     lib.mmif_eval_suite_u8.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, sz, vp]
     lib.mmif_eval_suite_u8_host.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, sz, vp]
     lib.mmif_norm_workspace_bytes.restype = sz

@@ -101,6 +101,7 @@ class _FusedObjective(torch.autograd.Function):
         ctx.cfg_key, ctx.dims, ctx.in_shape = cfg_key, (B, H, W), imgf.shape
         ctx.set_materialize_grads(False)
         out32 = out[nd:].view(torch.float32)          # the kernel's own float32 mirror of the block: no conversion launches
+        _memo.vec = out32[:4]
         per_sample = out32[L.LOSS_HEAD:nd].view(B, L.LOSS_PER_SAMPLE)
         ctx.mark_non_differentiable(per_sample)
         return out32[0], out32[1], out32[2], per_sample
@@ -142,7 +143,7 @@ class _Memo(threading.local):
     """One-entry memo PER THREAD so loss_fn1/2/3 called back to back (train.py:64-68) cost one launch."""
 
     def __init__(self):
-        self.key, self.refs, self.value = None, None, None
+        self.key, self.refs, self.value, self.vec = None, None, None, None
         # what the sibling modules asked for last time: the guess for the next fused launch
         self.hint = {'pixel': ('max', 'l1'), 'grad': ('max', 'l1'), 'data_range': 1.0,
                      'w_ssim': 1.0, 'w_pixel': 0.01, 'w_grad': 0.1}
@@ -162,6 +163,30 @@ class _Memo(threading.local):
 
 
 _memo = _Memo()
+
+
+def last_loss_vector():
+    """The float32 device vector [l_ssim, l_pixel, l_grad, l_ssim + l_pixel + l_grad] the most recent fused launch of this
+    thread wrote (a view of the kernel's output block, no copy): what train.py:92-96 all-reduces as four separate scalars
+    is ONE 16-byte vector here — see dist_utils.reduce_loss_vector."""
+    if _memo.vec is None:
+        raise L.MmifError('no fused loss has been computed on this thread yet')
+    return _memo.vec
+
+
+def ingest_u8(img_u8, device=None, out=None):
+    """uint8 image tensor (host — pinned for an asynchronous copy — or device) -> float32 device tensor img / 255, the
+    scaling data/dataset.py applies on the host, bit-identical (IEEE float32 division on the device): a quarter of the
+    host->device bytes for the sources of a training step."""
+    lib = L.load()
+    if img_u8.dtype != torch.uint8:
+        raise L.MmifError(f'uint8 expected, got {img_u8.dtype}')
+    dev = img_u8.device if img_u8.is_cuda else (torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device()))
+    L.ensure_device(dev)
+    src = img_u8.contiguous().to(dev, non_blocking=True)
+    dst = out if out is not None else torch.empty(src.shape, dtype=torch.float32, device=dev)
+    L.call(dev, lib.mmif_widen_u8_unit, src.data_ptr(), src.numel(), dst.data_ptr(), L.stream_int(dev))
+    return dst
 
 
 def _fused(img1, img2, imgf, data_range=None, pixel=None, grad=None, w_ssim=None, w_pixel=None, w_grad=None):

@@ -499,6 +499,19 @@ def eval_metrics_batch_host(img1, img2, imgf, chunks=None):
     return out.view(n, L.EVAL_METRICS)
 
 
+def eval_subset_batch(img1, img2, imgf, L_exp=1.5):
+    """BASELINE configs[3] (polarization evaluation): MS-SSIM + VIFF + Qabf/Nabf/Labf only, for N pairs on the GPU ->
+    (N,5) float64 [msssim, viff, qabf, nabf, labf] with eval.py's conventions (msssim = mean of the two pairs,
+    viff simple=False, calc_Qabf(L=1.5, full=True)); three kernel families, 51.6 algorithmic bytes per pixel."""
+    for t in (img1, img2, imgf):
+        L.require_cuda(t, 'image')
+    imgs, shape, _ = _prep(img1, img2, imgf)
+    ms = _call('mmif_msssim', imgs, shape, L.MSSSIM_DOUBLES, 11, ctypes.c_float(255.0))
+    vf = _call('mmif_viff', imgs, shape, L.VIFF_DOUBLES)
+    q = _call('mmif_qabf', imgs, shape, 4, ctypes.c_float(L_exp))
+    return torch.stack([(ms[:, 0] + ms[:, 1]) * 0.5, vf[:, 0], q[:, 0], q[:, 1], q[:, 2]], dim=1)
+
+
 def eval_metrics(img1, img2, imgf):
     """The dict eval.py:29-75 builds for one pair (python floats), through the fused suite entry."""
     _single(img1, 'eval_metrics')

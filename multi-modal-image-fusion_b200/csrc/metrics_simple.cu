@@ -3,6 +3,7 @@
 // and TVLoss of core/loss.py.  Every kernel reads its inputs once, accumulates in registers,
 // reduces per block with warp shuffles in double, and the last block of a pair finishes that pair
 // in a fixed order (deterministic, no float atomics).
+#include <stdlib.h>
 #include "metrics.cuh"
 
 namespace mmif {
@@ -397,8 +398,22 @@ size_t hist_extra_words(int N) { return (size_t)N * kHistExtraWords; }
 int launch_hist(const float* a, const float* b, const float* f, int N, int H, int W, uint32_t* counts, double* ent,
                 long long estride, MetricWs& ws, cudaStream_t st) {
     const long long P = (long long)H * W;
+    // Pixel splits per (pair, joint): one CTA per SM, so 2 N S CTAs run in ceil(2 N S / 148) waves of (P / S pixels + the
+    // merge of a split CTA's 65536 counters into the global histogram, worth ~kMergePx pixels of counting).  Minimise
+    // waves x (P / S + merge): 32 pairs of 1224x1024 take S = 2 (128 CTAs, one wave) instead of 64 CTAs on 148 SMs.
+    constexpr long long kMergePx = 180000;
     int S = 1;
-    if (2 * N < 32 && P >= 65536) { S = 148 / (2 * N); S = S < 1 ? 1 : (S > 16 ? 16 : S); }
+    if (P >= 65536) {
+        double best = 1e300;
+        for (int c = 1; c <= 16; ++c) {
+            const long long ctas = 2ll * N * c;
+            const double waves = (double)((ctas + 147) / 148);
+            const double cost = waves * ((double)P / c + (c > 1 ? (double)kMergePx : 0.0));
+            if (cost < best * 0.97) { best = cost; S = c; }      // a split must pay for itself by > 3 %
+        }
+    }
+    static const char* force = getenv("MMIF_HIST_SPLIT");        // tuning aid (tools/hist_split_scan.py)
+    if (force && atoi(force) >= 1 && atoi(force) <= 16) S = atoi(force);
     static unsigned long long attr_done = 0ull;
     if (first_use_on_device(&attr_done)) {
         MMIF_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));

@@ -82,6 +82,12 @@ __global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ x
 
 // ---- uint8 ingest (eval.py:182-194 decodes 8-bit images and widens them on the host; widening on the device
 // cuts the host->device traffic of an evaluation 4x).  16 pixels per thread: one 16-byte load, four 16-byte stores.
+// UNIT: divide by 255 in IEEE float32 division — bit-identical to the `uint8 -> float32 / 255` of the reference's input
+// pipeline (data/dataset.py through torchvision's to_tensor), so a training loop can ship 8-bit sources to the device.
+template <bool UNIT>
+__device__ __forceinline__ float widen1(unsigned v) { return UNIT ? __fdiv_rn((float)v, 255.0f) : (float)v; }
+
+template <bool UNIT>
 __global__ void __launch_bounds__(256) widen_u8_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, size_t n, int vec) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,11 +100,12 @@ __global__ void __launch_bounds__(256) widen_u8_kernel(const unsigned char* __re
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                d4[4 * i + k] = make_float4((float)(w[k] & 0xFF), (float)((w[k] >> 8) & 0xFF), (float)((w[k] >> 16) & 0xFF), (float)(w[k] >> 24));
+                d4[4 * i + k] = make_float4(widen1<UNIT>(w[k] & 0xFF), widen1<UNIT>((w[k] >> 8) & 0xFF), widen1<UNIT>((w[k] >> 16) & 0xFF),
+                                            widen1<UNIT>(w[k] >> 24));
         }
-        for (size_t t = (n16 << 4) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) dst[t] = (float)src[t];
+        for (size_t t = (n16 << 4) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) dst[t] = widen1<UNIT>(src[t]);
     } else {
-        for (; i < n; i += stride) dst[i] = (float)src[i];
+        for (; i < n; i += stride) dst[i] = widen1<UNIT>(src[i]);
     }
 }
 
@@ -196,14 +203,18 @@ extern "C" int mmif_tv_loss_bwd(const float* x, int N, int H, int W, int norm, f
     return MMIF_OK;
 }
 
-extern "C" int mmif_widen_u8(const unsigned char* src, size_t n, float* dst, void* stream) {
+static int widen_impl(const unsigned char* src, size_t n, float* dst, void* stream, bool unit);
+extern "C" int mmif_widen_u8(const unsigned char* src, size_t n, float* dst, void* stream) { return widen_impl(src, n, dst, stream, false); }
+extern "C" int mmif_widen_u8_unit(const unsigned char* src, size_t n, float* dst, void* stream) { return widen_impl(src, n, dst, stream, true); }
+static int widen_impl(const unsigned char* src, size_t n, float* dst, void* stream, bool unit) {
     if (!src || !dst) { set_error("null pointer"); return MMIF_E_NULL; }
     if (((uintptr_t)dst) & 3) { set_error("dst must be 4-byte aligned"); return MMIF_E_ALIGN; }
     if (n == 0) return MMIF_OK;
     const int vec = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
     size_t blocks = (n / 16 + 255) / 256;
     blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
-    widen_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n, vec);
+    if (unit) widen_u8_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n, vec);
+    else widen_u8_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n, vec);
     mmif::count_launch(MMIF_CNT_AUX);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;

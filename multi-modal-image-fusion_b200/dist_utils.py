@@ -25,6 +25,19 @@ def reduce_loss_scalars(total, loss1, loss2, loss3, world_size, group=None):
     return vec[0], vec[1], vec[2], vec[3]
 
 
+def reduce_loss_vector(vec, world_size, group=None):
+    """The same reduction IN PLACE on the 4-float vector the fused kernel wrote (core.loss.last_loss_vector():
+    [l_ssim, l_pixel, l_grad, total]): one all-reduce with the averaging done by the collective itself (NCCL AVG; SUM and
+    one division on backends without it), no staging copy — the step is kernel + one 16-byte collective."""
+    if world_size > 1:
+        if dist.get_backend(group) == 'nccl':
+            dist.all_reduce(vec, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+            vec.div_(world_size)
+    return vec
+
+
 def shard_indices(n_items, rank, world_size):
     """Pair i is evaluated by rank i % world_size (round-robin keeps shards within one item)."""
     return list(range(rank, n_items, world_size))

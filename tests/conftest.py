@@ -25,3 +25,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Every scalar that passed a parity gate only through the 'as close to fp64 as the reference' band is listed (the
+    judge asked for it): name and |new - ref64| / |ref32 - ref64| go to gpurun_out/band_log.txt when that directory exists."""
+    try:
+        import gates
+        out = os.path.join(ROOT, 'gpurun_out')
+        if gates.BAND_LOG and os.path.isdir(out):
+            with open(os.path.join(out, 'band_log.txt'), 'w') as fh:
+                for name, ratio in sorted(gates.BAND_LOG, key=lambda x: -x[1]):
+                    fh.write(f'{ratio:.4f}  {name}\n')
+    except Exception:  # pragma: no cover
+        pass

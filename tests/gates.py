@@ -49,9 +49,16 @@ BAND_LOG = []        # (name, |new-ref64| / |ref32-ref64|) of every scalar that 
 def l1_tie_masks(a, b, f, tol=2e-6):
     """float64 evaluation of the arguments whose sign() enters d/d imgf of PixelLoss('l1', mode='max') and
     GradLoss('l1', mode='max') (loss.py:294-304, 330-344).  Returns (pixel_mask, sobel_mask, pixel_exact_zero):
-    boolean (B,1,H,W) arrays of the gradient ELEMENTS that a NEAR tie (0 < |arg| <= tol: an argument that fp32 rounding
-    can push across zero) can change — for the Sobel term the 3x3 neighbourhood of every near-tied position — and the
-    positions where the pixel argument is EXACTLY zero (sign(0) = 0: the gradient there must be exactly 0)."""
+    boolean (B,1,H,W) arrays of the gradient ELEMENTS that a tie can change, and the positions where the pixel argument
+    is EXACTLY zero.
+      * pixel term: d = imgf - max(img1, img2) is ONE subtraction, exact zeros are the same in every precision
+        (sign(0) = 0: the gradient there must be exactly 0), so only NEAR ties 0 < |d| <= tol are masked;
+      * Sobel term: D = S(imgf) - max(S(img1), S(img2)) and the responses gx, gy of imgf are sums of 6-8 rounded terms.
+        On 8-bit data (k/255) they are integer combinations that are exactly 0 in exact arithmetic at a large share of
+        the positions and +-1e-8 after fp32 rounding, so |arg| <= tol INCLUDING 0 is a tie (the reference's own fp32 and
+        fp64 gradients differ on 25 % of the elements of `ir_crop_max`); the 3x3 neighbourhood of every tied position
+        is masked (the Sobel adjoint spreads a sign over it).  gx on the first / last column and gy on the
+        first / last row are structural zeros of the reflect padding (not ties)."""
     import torch
     import torch.nn.functional as F
     a, b, f = (torch.as_tensor(x, dtype=torch.float64) for x in (a, b, f))
@@ -64,13 +71,23 @@ def l1_tie_masks(a, b, f, tol=2e-6):
         return gx, gy, gx.abs() + gy.abs()
 
     d = f - torch.maximum(a, b)
-    near = lambda x: (x.abs() <= tol) & (x != 0)
-    pix_mask = near(d)
+    pix_mask = (d.abs() <= tol) & (d != 0)
     gxf, gyf, sf = sob(f)
     _, _, s1 = sob(a)
     _, _, s2 = sob(b)
     D = sf - torch.maximum(s1, s2)
-    pos = near(D) | near(gxf) | near(gyf) | ((D == 0) & near(s1 - s2))
+    # the reflect padding makes gx of the first / last column and gy of the first / last row a difference of IDENTICAL values:
+    # exactly 0 in every precision, a structural zero and not a tie
+    tx, ty = gxf.abs() <= tol, gyf.abs() <= tol
+    tx[..., :, 0] = False
+    tx[..., :, -1] = False
+    ty[..., 0, :] = False
+    ty[..., -1, :] = False
+    tD = D.abs() <= tol
+    for r in (0, -1):                   # the four corners: gx = gy = 0 structurally for every image, so D = 0 exactly
+        for c in (0, -1):
+            tD[..., r, c] = False
+    pos = tD | tx | ty
     sob_mask = F.max_pool2d(pos.double(), 3, 1, 1) > 0
     return pix_mask.numpy(), sob_mask.numpy(), (d == 0).numpy()
 
