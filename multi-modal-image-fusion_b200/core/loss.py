@@ -279,6 +279,27 @@ class _WeightedSSIM(torch.autograd.Function):
         return None, None, dF.view(ctx.in_shape), None
 
 
+class _PlainSSIM(torch.autograd.Function):
+    """mean_b (ssim(img1, imgf) + ssim(img2, imgf)) / 2 with gradient w.r.t. imgf: the SSIM-only kernels (no pixel /
+    Sobel work) — what SSIMLoss('ssim', use_padding=True) needs after its reflect padding."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, imgf, data_range):
+        x1, x2, y = _prep3(img1, img2, imgf)
+        ps = _fwd_per_sample(x1, x2, y, data_range).to(torch.float32)
+        ctx.save_for_backward(x1, x2, y)
+        ctx.data_range, ctx.in_shape = data_range, imgf.shape
+        return (ps[:, 0].mean() + ps[:, 3].mean()) * 0.5
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, y = ctx.saved_tensors
+        g1 = g.to(torch.float32).reshape(1).contiguous()
+        pw = torch.full((y.shape[0], 2), 0.5, dtype=torch.float32, device=y.device)
+        dF = _ssim_bwd_ex(x1, x2, y, ctx.data_range, g1, pw, 0, 1.0 / y.shape[0])
+        return None, None, dF.view(ctx.in_shape), None
+
+
 class _SSIMDict(torch.autograd.Function):
     """SSIM.forward (loss.py:163-185 -> calc_ssim, loss.py:52-110) with size_average=True, differentiable:
     (img1, img2) -> per-sample (ssim, cs, sigma).  SSIM and CS are symmetric in their arguments, so the gradient
@@ -633,6 +654,9 @@ class MSW_SSIM(nn.Module):
     def forward(self, img1, img2, imgf):
         if any(k not in (11, 9, 7, 5, 3) for k in self.win_sizes):
             raise NotImplementedError('MSW_SSIM: windows 11, 9, 7, 5, 3 are built')
+        if self.size_average:
+            raise NotImplementedError('MSW_SSIM(size_average=True) (per-sample gamma from the window means) is not built; '
+                                      'SSIMLoss("msw-ssim") and the class default use size_average=False')
         dr = _auto_range(img1) if self.data_range is None else self.data_range
         return _MSWSSIM.apply(img1, img2, imgf, dr, tuple(self.win_sizes), bool(self.use_padding))
 
@@ -652,6 +676,8 @@ class SSIMLoss(nn.Module):
             img1, img2, imgf = _pad3(img1, img2, imgf)      # reflect pad 5, then the valid-window path (loss.py:45-47)
         dr = _auto_range(img1) if self.data_range is None else self.data_range     # loss.py:60-65
         if self.mode == 'ssim':
+            if self.use_padding:        # SSIM-only kernels on the padded images (the fused objective's other terms are not wanted)
+                return self.weight * (1.0 - _PlainSSIM.apply(img1, img2, imgf, dr))
             loss, _, _, _ = _fused(img1, img2, imgf, data_range=dr, w_ssim=self.weight)
             return loss
         elif self.mode == 'w-ssim':

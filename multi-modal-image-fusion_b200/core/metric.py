@@ -74,7 +74,9 @@ def _prep(*imgs):
 
 
 class _PairMemo:
-    """Results of one kernel family for one (a, b, f) triple, keyed on storage identity/version."""
+    """Results of one kernel family for one (a, b, f) triple, keyed on storage identity/version.  A result whose caller
+    lives on the CPU (eval.py) is copied to the host ONCE per family (`host`), so the ~25 calc_* calls of one pair cost one
+    device->host transfer + sync per kernel family instead of one per returned scalar."""
 
     def __init__(self, cap=12):
         self.cap, self.items = cap, []
@@ -85,17 +87,92 @@ class _PairMemo:
 
     def get(self, kind, tensors, extra, compute):
         key = self._key(kind, tensors, extra)
-        for k, refs, val in self.items:
-            if k == key and all(r() is t for r, t in zip(refs, tensors)):
-                return val
-        val = compute()
-        self.items.append((key, tuple(weakref.ref(t) for t in tensors), val))
+        for ent in self.items:
+            if ent[0] == key and all(r() is t for r, t in zip(ent[1], tensors)):
+                return ent
+        ent = [key, tuple(weakref.ref(t) for t in tensors), compute(), None]
+        self.items.append(ent)
         if len(self.items) > self.cap:
             self.items.pop(0)
-        return val
+        return ent
 
 
 _memo = _PairMemo()
+
+
+def _rows(ent, home, part=None):
+    """The (n, K) float64 rows of a memo entry where the caller lives: the device tensor, or its single host copy."""
+    val = ent[2] if part is None else ent[2][part]
+    if home.type != 'cpu':
+        return val if val.device == home else val.to(home)
+    if ent[3] is None:
+        ent[3] = {}
+    if part not in ent[3]:
+        ent[3][part] = val.cpu()
+    return ent[3][part]
+
+
+class _Triples:
+    """eval.py:29-75 calls the one- and two-image functions (calc_std(f), calc_mse(a, f), calc_mse(b, f), calc_cc, ...) one
+    after another on the SAME three tensors.  The kernels are three-image kernels, so once the triple (a, b, f) is known
+    — from any three-image call, or from two two-image calls (x, f), (x', f) on one fused image — every later call on its
+    members is served by ONE launch per kernel family on (a, b, f) instead of one launch per distinct argument list."""
+
+    def __init__(self, cap=4):
+        self.cap, self.triples, self.pending = cap, [], []       # entries: tuples of (weakref, version)
+
+    @staticmethod
+    def _same(entry, t):
+        return entry[0]() is t and entry[1] == t._version
+
+    @staticmethod
+    def _mk(t):
+        return (weakref.ref(t), t._version)
+
+    def add(self, a, b, f):
+        for tr in self.triples:
+            if self._same(tr[0], a) and self._same(tr[1], b) and self._same(tr[2], f):
+                return
+        self.triples.append((self._mk(a), self._mk(b), self._mk(f)))
+        if len(self.triples) > self.cap:
+            self.triples.pop(0)
+
+    def _live(self, tr):
+        t = tuple(e[0]() for e in tr)
+        return t if all(x is not None and x._version == e[1] for x, e in zip(t, tr)) else None
+
+    def of_fused(self, f):
+        """-> (a, b, f) of the most recent triple whose fused image is `f`, or None."""
+        for tr in reversed(self.triples):
+            if self._same(tr[2], f):
+                t = self._live(tr)
+                if t is not None:
+                    return t
+        return None
+
+    def of_pair(self, x, f):
+        """(x, f) -> ((a, b, f), slot) with x == a (slot 0) or x == b (slot 1); learns the triple from the second distinct
+        source seen with the same fused image; (None, 0) while only one source is known."""
+        if x.shape != f.shape:
+            return None, 0
+        for tr in reversed(self.triples):
+            if self._same(tr[2], f) and (self._same(tr[0], x) or self._same(tr[1], x)):
+                t = self._live(tr)
+                if t is not None:
+                    return t, (0 if t[0] is x else 1)
+        for px, pf in reversed(self.pending):
+            if self._same(pf, f) and not self._same(px, x):
+                other = px[0]()
+                if other is not None and other._version == px[1] and other.shape == x.shape and other.device == x.device:
+                    self.add(other, x, f)
+                    return (other, x, f), 1
+        self.pending.append((self._mk(x), self._mk(f)))
+        if len(self.pending) > self.cap:
+            self.pending.pop(0)
+        return None, 0
+
+
+_triples = _Triples()
 
 
 def _ws(dev, n, h, w):
@@ -112,9 +189,8 @@ def _call(fn_name, imgs, shape, out_doubles, *extra_args):
     dev = imgs[0].device
     out = torch.empty(n * out_doubles, dtype=torch.float64, device=dev)
     ws = _ws(dev, n, h, w)
-    with torch.cuda.device(dev):
-        L.check(getattr(lib, fn_name)(imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, *extra_args,
-                                      out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+    L.call(dev, getattr(lib, fn_name), imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, *extra_args,
+           out.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_int(dev))
     return out.view(n, out_doubles)
 
 
@@ -125,7 +201,8 @@ def _stats(a, b, f):
     return _memo.get('stats', (a, b, f), None, run)
 
 
-def _hist(a, b, f, want_counts=False):
+def _hist(a, b, f):
+    """memo entry whose value is (counts (n, HIST_WORDS) int32, entropies (n, EN_COUNT) float64)."""
     def run():
         lib = L.load()
         imgs, (n, h, w), _ = _prep(a, b, f)
@@ -133,18 +210,36 @@ def _hist(a, b, f, want_counts=False):
         counts = torch.empty(n * L.HIST_WORDS, dtype=torch.int32, device=dev)
         ent = torch.empty(n * L.EN_COUNT, dtype=torch.float64, device=dev)
         ws = _ws(dev, n, h, w)
-        with torch.cuda.device(dev):
-            L.check(lib.mmif_hist(imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, counts.data_ptr(),
-                                  ent.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)))
+        L.call(dev, lib.mmif_hist, imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), n, h, w, counts.data_ptr(),
+               ent.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_int(dev))
         return counts.view(n, L.HIST_WORDS), ent.view(n, L.EN_COUNT)
     return _memo.get('hist', (a, b, f), None, run)
+
+
+def hist_raw(a, b, f):
+    """(counts (n, MMIF_HIST_WORDS) int32, entropies (n, MMIF_EN_COUNT) float64) device tensors of mmif_hist."""
+    return _hist(a, b, f)[2]
 
 
 def _qabf(a, b, f, Lexp):
     def run():
         imgs, shape, _ = _prep(a, b, f)
         return _call('mmif_qabf', imgs, shape, 4, ctypes.c_float(Lexp))
+    _triples.add(a, b, f)
     return _memo.get('qabf', (a, b, f), float(Lexp), run)
+
+
+def _one(f):
+    """Arguments for a one-image call on `f`: the known triple that has it as its fused image, else (f, f, f)."""
+    tr = _triples.of_fused(f)
+    return tr if tr is not None else (f, f, f)
+
+
+def _two(x, f):
+    """Arguments + slot for a two-image call (x, f): the known triple (slot 0: x is its first source, 1: its second),
+    else (x, x, f) with slot 0."""
+    tr, slot = _triples.of_pair(x, f)
+    return (tr, slot) if tr is not None else ((x, x, f), 0)
 
 
 def _pad_dev(t, pad):
@@ -213,17 +308,17 @@ def _msssim2(a, b, f, win_size, data_range, use_padding):
 
 
 def _viff3(a, b, f):
+    _triples.add(a, b, f)
+
     def run():
         imgs, shape, _ = _prep(a, b, f)
         return _call('mmif_viff', imgs, shape, L.VIFF_DOUBLES)
     return _memo.get('viff', (a, b, f), None, run)
 
 
-def _scalar(row_value, home, dtype=torch.float32):
-    """0-dim tensor on the caller's device (the global mean over all pairs in the batch is what
-    the reference computes for N>1; these drop-ins are called with N == 1 by every script)."""
-    v = row_value.to(dtype)
-    return v.to(home) if v.device != home else v
+def _scalar(rows, idx, dtype=torch.float32):
+    """0-dim tensor rows[0, idx] in the reference's dtype, on the device `rows` lives on (the caller's)."""
+    return rows[0, idx].to(dtype)
 
 
 def _single(t, what):
@@ -232,34 +327,41 @@ def _single(t, what):
                                   'use eval_metrics_batch for batches')
 
 
+def _stat1(img, idx_f, idx_a, idx_b):
+    """A one-image statistic of `img`: column idx_f of the triple that has it as fused image, else of (img, img, img)."""
+    tr = _one(img)
+    return _scalar(_rows(_stats(*tr), img.device), idx_f)
+
+
 # 1. mean
 def calc_mean(img):
     _single(img, 'calc_mean')
-    return _scalar(_stats(img, img, img)[0, 0], img.device)
+    return _stat1(img, 0, 9, 10)
 
 
 # 2. sd
 def calc_std(img):
     _single(img, 'calc_std')
-    return _scalar(_stats(img, img, img)[0, 1], img.device)
+    return _stat1(img, 1, 11, 12)
 
 
 # 3. ag
 def calc_ag(img):
     _single(img, 'calc_ag')
-    return _scalar(_stats(img, img, img)[0, 2], img.device)
+    return _stat1(img, 2, None, None)
 
 
 # 4. sf
 def calc_sf(img):
     _single(img, 'calc_sf')
-    return _scalar(_stats(img, img, img)[0, 3], img.device)
+    return _stat1(img, 3, None, None)
 
 
-# 5. mse  (kernel slot: a vs f)
+# 5. mse  (kernel slots: a vs f = column 4, b vs f = column 5)
 def calc_mse(img1, img2):
     _single(img1, 'calc_mse')
-    return _scalar(_stats(img1, img1, img2)[0, 4], img1.device)
+    tr, slot = _two(img1, img2)
+    return _scalar(_rows(_stats(*tr), img1.device), 4 + slot)
 
 
 # 6. psnr — pure scalar arithmetic on the mse tensor, as in the reference (metric.py:72-76)
@@ -272,53 +374,57 @@ def calc_psnr(mse, L=1.0, root=False):
 # 7. cc
 def calc_cc(img1, img2):
     _single(img1, 'calc_cc')
-    return _scalar(_stats(img1, img1, img2)[0, 6], img1.device)
+    tr, slot = _two(img1, img2)
+    return _scalar(_rows(_stats(*tr), img1.device), 6 + slot)
 
 
 # 8. scd
 def calc_scd(img1, img2, imgf):
     _single(img1, 'calc_scd')
-    return _scalar(_stats(img1, img2, imgf)[0, 8], img1.device)
+    _triples.add(img1, img2, imgf)
+    return _scalar(_rows(_stats(img1, img2, imgf), img1.device), 8)
 
 
 # 9. en
 def calc_entropy(img):
     _single(img, 'calc_entropy')
-    return _scalar(_hist(img, img, img)[1][0, 2], img.device)
+    tr = _one(img)
+    return _scalar(_rows(_hist(*tr), img.device, 1), 2)
 
 
 # 11. ce
 def calc_cross_ent(img1, img2):
     _single(img1, 'calc_cross_ent')
-    return _scalar(_hist(img1, img1, img2)[1][0, 5], img1.device)
+    tr, slot = _two(img1, img2)
+    return _scalar(_rows(_hist(*tr), img1.device, 1), 5 + slot)
 
 
 # 12. mi — float64 like the reference (metric.py:179-188)
 def calc_mul_info(img1, img2, normalized=False):
     _single(img1, 'calc_mul_info')
-    ent = _hist(img1, img1, img2)[1]
-    return _scalar(ent[0, 9] if normalized else ent[0, 7], img1.device, torch.float64)
+    tr, slot = _two(img1, img2)
+    return _scalar(_rows(_hist(*tr), img1.device, 1), (9 if normalized else 7) + slot, torch.float64)
 
 
 # 13. Qabf
 def calc_Qabf(img1, img2, imgf, L=1.5, full=False):
     _single(img1, 'calc_Qabf')
-    q = _qabf(img1, img2, imgf, L)
+    q = _rows(_qabf(img1, img2, imgf, L), img1.device)
     if full:
-        return tuple(_scalar(q[0, i], img1.device) for i in range(3))
-    return _scalar(q[0, 0], img1.device)
+        return tuple(_scalar(q, i) for i in range(3))
+    return _scalar(q, 0)
 
 
 # 14. Nabf
 def calc_Nabf(img1, img2, imgf, L=1.5, modified=True):
     _single(img1, 'calc_Nabf')
-    return _scalar(_qabf(img1, img2, imgf, L)[0, 1 if modified else 3], img1.device)
+    return _scalar(_rows(_qabf(img1, img2, imgf, L), img1.device), 1 if modified else 3)
 
 
 # 15. Labf
 def calc_Labf(img1, img2, imgf, L=1.5):
     _single(img1, 'calc_Labf')
-    return _scalar(_qabf(img1, img2, imgf, L)[0, 2], img1.device)
+    return _scalar(_rows(_qabf(img1, img2, imgf, L), img1.device), 2)
 
 
 # 16. ssim
@@ -326,10 +432,11 @@ def calc_ssim(img1, img2, win_size=11, data_range=255.0, use_padding=False, size
     _single(img1, 'calc_ssim')
     if not size_average:
         return _ssim_map(img1, img2, win_size, data_range, use_padding, full)
-    r = _ssim2(img1, img1, img2, win_size, data_range, use_padding)
+    tr, slot = _two(img1, img2)
+    r = _rows(_ssim2(*tr, win_size, data_range, use_padding), img1.device)
     if full:
-        return _scalar(r[0, 0], img1.device), _scalar(r[0, 1], img1.device)
-    return _scalar(r[0, 0], img1.device)
+        return _scalar(r, 2 * slot), _scalar(r, 2 * slot + 1)
+    return _scalar(r, 2 * slot)
 
 
 def _ssim_map(img1, img2, win_size, data_range, use_padding, full):
@@ -356,13 +463,14 @@ def _ssim_map(img1, img2, win_size, data_range, use_padding, full):
 # 17. msssim
 def calc_msssim(img1, img2, win_size=11, data_range=255.0, use_padding=False):
     _single(img1, 'calc_msssim')
-    return _scalar(_msssim2(img1, img1, img2, win_size, data_range, use_padding)[0, 0], img1.device)
+    tr, slot = _two(img1, img2)
+    return _scalar(_rows(_msssim2(*tr, win_size, data_range, use_padding), img1.device), slot)
 
 
 # 18. viff
 def calc_viff(img1, img2, imgf, simple=True):
     _single(img1, 'calc_viff')
-    return _scalar(_viff3(img1, img2, imgf)[0, 1 if simple else 0], img1.device)
+    return _scalar(_rows(_viff3(img1, img2, imgf), img1.device), 1 if simple else 0)
 
 
 # ---- batched entries (not in the reference; used by the sharded evaluation and the benchmark) ----
@@ -523,6 +631,6 @@ def eval_metrics(img1, img2, imgf):
 def histograms(img1, img2, imgf):
     """Integer counts (hist_a, hist_b, hist_f, joint_af, joint_bf) of one pair, as int64 CPU tensors."""
     _single(img1, 'histograms')
-    c = _hist(img1, img2, imgf)[0][0].to(torch.int64).cpu()
+    c = _hist(img1, img2, imgf)[2][0][0].to(torch.int64).cpu()
     return (c[0:256], c[256:512], c[512:768], c[768:768 + 65536].view(256, 256),
             c[768 + 65536:].view(256, 256))

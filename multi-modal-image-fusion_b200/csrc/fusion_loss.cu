@@ -356,10 +356,13 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
                         cc[j] = vj ? ch : f2(0.f, 0.f);
                     }
                     if (ZMODE) {
-                        const float2 zf = bcast(((zm >> j) & 1u) ? 1.f : 0.f);      // (masked columns hold finite values: zero-filled data, C1, C2 > 0)
-                        z_ss = fma2(zf, S, z_ss);
-                        z_cs = fma2(zf, Cs, z_cs);
-                        z_sg = fma2(zf, max2(vk, 1e-4f), z_sg);
+                        // SELECT, never multiply by 0: the two window columns past the strip read the never-written pad
+                        // columns of vbuf, whose stale bits can be NaN / Inf (0 * NaN = NaN poisoned the loss sums)
+                        const bool zq = (zm >> j) & 1u;
+                        const float2 sg = max2(vk, 1e-4f);
+                        z_ss = add2(z_ss, f2(zq ? S.x : 0.f, zq ? S.y : 0.f));
+                        z_cs = add2(z_cs, f2(zq ? Cs.x : 0.f, zq ? Cs.y : 0.f));
+                        z_sg = add2(z_sg, f2(zq ? sg.x : 0.f, zq ? sg.y : 0.f));
                     }
                 }
             } else {

@@ -424,6 +424,8 @@ static int run_vif(const float* a, const float* b, const float* f, int N, int H,
         memset(&L, 0, sizeof(L));
         L.win = k; L.sigma = (double)k / 5.0; L.epi = EPI_VIF; L.finalize = FIN_SUMS; L.data_range = 255.f;
         L.cfg.pixel_norm = L.cfg.grad_norm = MMIF_NORM_L1;
+        static const char* vif_eps = getenv("MMIF_VIF_EPS_EMULATION");      // experiment switch, see DESIGN.md section 2
+        L.plain_moments = (vif_eps && atoi(vif_eps) == 1) ? 0 : 1;
         int rc = launch_moment_fwd(L, ca, cb, cf, N, d.h[s], d.w[s], raw + s * 8, stride, nullptr, ws.fwd_ws, ws.fwd_ws_bytes, st);
         if (rc) return rc;
     }

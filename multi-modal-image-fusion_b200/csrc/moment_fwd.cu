@@ -80,6 +80,7 @@ int launch_moment_fwd(const FwdLaunch& L, const float* x1, const float* x2, cons
     p.do_sobel = L.do_sobel;
     for (int i = 0; i < 6; ++i) p.maps[i] = L.maps[i];
     p.denorm = L.denorm;
+    p.plain_moments = L.plain_moments;
     unsigned char* w8 = (unsigned char*)ws;
     p.fin.B = B; p.fin.H = H; p.fin.W = W; p.fin.Hout = g.Hout; p.fin.Wout = g.Wout;
     p.fin.finalize = L.finalize;

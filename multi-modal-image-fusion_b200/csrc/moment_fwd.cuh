@@ -121,6 +121,7 @@ struct FwdParams {
     int do_sobel;            // EPI_SSIM only: also accumulate the Sobel / pixel terms
     float* maps[6];          // EPI_MAPS: [ssim1, cs1, sigma1, ssim2, cs2, sigma2] maps [B][Hout][Wout] (each may be NULL)
     unsigned char* denorm;   // do_sobel: also store uint8(clip(y, 0, 1) * 255) [B][H][W] (test.py:70-73 post-step) or NULL
+    int plain_moments;       // 1: exact central moments (window sum taken as 1: no eps / rho emulation of the reference's fp32 window)
 };
 
 static inline size_t ws_counters_bytes(int B) { return (size_t)(((B + 1) * 4 + 255) / 256) * 256; }
@@ -256,7 +257,8 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
         mbar_fence_init();
     }
     __syncthreads();
-    const Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, i0, rows_out + HALO, j0, p.taps);
+    Shift sh = tile_shift(sm, src.img[0], src.img[1], src.img[2], p.H, p.W, i0, rows_out + HALO, j0, p.taps);
+    if (p.plain_moments) sh = make_shift(sh.c.x, sh.c.y, sh.cy, 1.f, 0.f, 0.f);
 
     ring_issue(sm, src, &map1, &map2, &mapy, 0);
     ring_issue(sm, src, &map1, &map2, &mapy, 1);
@@ -383,6 +385,7 @@ struct FwdLaunch {
     MmifLossCfg cfg;         // combine / norm / weights (EPI_SSIM + do_sobel)
     float* maps[6];          // EPI_MAPS outputs
     unsigned char* denorm;   // do_sobel: uint8 image of y (or NULL)
+    int plain_moments;       // see FwdParams
 };
 int pick_seg_rows(int rows, int other_ctas, int slots, int extra_rows, double tail = 0.0);
 int fwd_seg_rows(int rows, int other_ctas);

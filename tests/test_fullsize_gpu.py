@@ -105,7 +105,7 @@ def test_polar_suite_invariants_at_full_batch():
     np.testing.assert_allclose(r[:, 10] + r[:, 11] + r[:, 12], 1.0, rtol=0, atol=2e-6)        # qabf + nabf + labf = 1
     one = MM.eval_metrics_batch(a[7:8], b[7:8], f[7:8])[0].cpu().numpy()
     np.testing.assert_allclose(r[7], one, rtol=2e-6, atol=1e-12)      # (segment geometry depends on the batch size)
-    counts, _ = MM._hist(a, b, f, want_counts=True)
+    counts, _ = MM.hist_raw(a, b, f)
     c = counts.to(torch.int64)
     assert (c[:, 0:256].sum(1) == h * w).all() and (c[:, 768:768 + 65536].sum(1) == h * w).all()
     assert torch.equal(c[:, 768:768 + 65536].view(n, 256, 256).sum(1), c[:, 512:768])       # f marginal = column sums of joint(a,f)

@@ -22,7 +22,7 @@ for (n, h, w) in ((21, 480, 640), (32, 1024, 1224), (4, 1024, 1224), (1, 1024, 1
     f = torch.floor((a + b) / 2)
     def hist():
         MM._memo.items.clear()
-        MM._hist(a, b, f)
+        MM.hist_raw(a, b, f)
     print('S=%%s %%dx%%dx%%d: hist %%.1f us  suite %%.1f us' %% (os.environ.get('MMIF_HIST_SPLIT', 'model'), n, h, w, t(hist), t(lambda: MM.eval_metrics_batch(a, b, f))))
 ''' % ROOT
 for s in (None, '1', '2', '3', '4', '6'):
