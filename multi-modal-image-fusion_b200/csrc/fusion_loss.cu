@@ -7,6 +7,9 @@
 //   fusion_loss_bwd : recomputes the moments, forms the per-window derivative coefficients, runs the
 //                     adjoint blur and the folded Sobel adjoint and writes dL/dIf once
 //                     (12 B read + 4 B written per pixel).  One launch.
+#include <stdlib.h>
+#include <queue>
+#include <vector>
 #include "moment_fwd.cuh"
 
 namespace mmif {
@@ -27,13 +30,116 @@ struct BG {
 };
 static int bwd_tg(int win) { const int halo = win - 1; return (kTWI - 2 * halo) / 4 * 4; }
 
-struct BwdGeom { int Hout, Wout, seg_rows, nseg, nstrip; };
+// Row segments of the backward / single-pass grid: the first n_tall segments are seg_rows high, the rest seg_short
+// (both multiples of 8; seg_short == seg_rows = the uniform scheme).  The grid is (strip, sample, segment) with the segment
+// index SLOWEST, so the hardware dispatcher hands out all tall segments of all samples first and the short ones last:
+// longest-processing-time-first list scheduling, which trims the partial last wave that costs a per-rank batch of 8
+// (304 columns on 296 CTA slots) 8 % in the uniform scheme.  Every sample and strip is cut the same way, so a sample's
+// result does not depend on its position in the batch.
+struct BwdGeom { int Hout, Wout, seg_rows, seg_short, n_tall, nseg, nstrip; };
+
+static int geom_nseg(int H, int T, int n_tall, int s) {
+    const int tall_rows = n_tall * T;
+    return tall_rows >= H ? ceil_div(H, T) : n_tall + ceil_div(H - tall_rows, s);
+}
+
+// Makespan (in row units) of `cols` columns cut into the given segments on 148 SMs x 2 slots, CTAs dispatched in launch
+// order to the first slot that frees; a CTA alone on its SM runs kSolo times faster (measured 1.39).  Event simulation.
+static double simulate_makespan(int H, int cols, int T, int n_tall, int s, int extra) {
+    constexpr int kSM = 148;
+    constexpr double kSolo = 1.39;
+    const int nseg = geom_nseg(H, T, n_tall, s);
+    const long long total = (long long)cols * nseg;
+    auto work_of = [&](long long idx) {          // launch order: segment slowest
+        const int seg = (int)(idx / cols);
+        int i0, i1;
+        if (seg < n_tall) { i0 = seg * T; i1 = i0 + T; } else { i0 = n_tall * T + (seg - n_tall) * s; i1 = i0 + s; }
+        if (i1 > H) i1 = H;
+        return (double)(i1 - i0 + extra);
+    };
+    double rem[kSM][2];
+    double now[kSM];
+    unsigned ver[kSM];
+    long long next = 0;
+    for (int k = 0; k < kSM; ++k) { rem[k][0] = rem[k][1] = 0.0; now[k] = 0.0; ver[k] = 0u; }
+    for (int slot = 0; slot < 2; ++slot)
+        for (int k = 0; k < kSM && next < total; ++k) rem[k][slot] = work_of(next++);
+    struct Ev { double t; int sm; int slot; unsigned ver; };
+    auto later = [](const Ev& a, const Ev& b) { return a.t > b.t; };
+    std::priority_queue<Ev, std::vector<Ev>, decltype(later)> pq(later);
+    auto push_next = [&](int k) {               // earliest completion on SM k under its current pairing
+        const bool a0 = rem[k][0] > 0.0, a1 = rem[k][1] > 0.0;
+        if (!a0 && !a1) return;
+        const double rate = (a0 && a1) ? 1.0 : kSolo;
+        const int slot = (a0 && (!a1 || rem[k][0] <= rem[k][1])) ? 0 : 1;
+        pq.push(Ev{now[k] + rem[k][slot] / rate, k, slot, ver[k]});
+    };
+    for (int k = 0; k < kSM; ++k) push_next(k);
+    double makespan = 0.0;
+    while (!pq.empty()) {
+        const Ev e = pq.top();
+        pq.pop();
+        if (e.ver != ver[e.sm]) continue;
+        const int k = e.sm;
+        const bool both = rem[k][0] > 0.0 && rem[k][1] > 0.0;
+        const double rate = both ? 1.0 : kSolo;
+        const double dt = e.t - now[k];
+        for (int slot = 0; slot < 2; ++slot)
+            if (rem[k][slot] > 0.0) rem[k][slot] -= dt * rate;
+        rem[k][e.slot] = 0.0;
+        now[k] = e.t;
+        makespan = e.t;
+        if (next < total) rem[k][e.slot] = work_of(next++);
+        ++ver[k];
+        push_next(k);
+    }
+    return makespan;
+}
+
 static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
     BwdGeom g;
     g.Hout = H - (win - 1); g.Wout = W - (win - 1);
     g.nstrip = ceil_div(W, bwd_tg(win));
-    g.seg_rows = pick_seg_rows(H, B * g.nstrip, 2 * 148, 2 * (win - 1) + 8, 0.72);   // 2 CTAs / SM; halo + batch rounding + prologue
-    g.nseg = ceil_div(H, g.seg_rows);
+    const int extra = 2 * (win - 1) + 8;                      // halo + batch rounding + prologue, in rows
+    g.seg_rows = pick_seg_rows(H, B * g.nstrip, 2 * 148, extra, 0.72);   // 2 CTAs / SM
+    g.seg_short = g.seg_rows; g.n_tall = ceil_div(H, g.seg_rows);
+    g.nseg = g.n_tall;
+    // memo: the search below simulates a few dozen schedules (~1 ms); a training loop asks for one shape
+    struct Key { int B, H, W, win; BwdGeom g; };
+    static thread_local Key memo[8];
+    static thread_local int memo_n = 0, memo_next = 0;
+    for (int i = 0; i < memo_n; ++i)
+        if (memo[i].B == B && memo[i].H == H && memo[i].W == W && memo[i].win == win) return memo[i].g;
+    const int cols = B * g.nstrip;
+    static const bool uniform_only = getenv("MMIF_UNIFORM_SEGMENTS") != nullptr;      // A/B switch for the measurements
+    if (!uniform_only && (long long)cols * g.nseg <= 40000 && g.seg_rows >= 32) {
+        double best = simulate_makespan(H, cols, g.seg_rows, g.n_tall, g.seg_rows, extra);
+        const BwdGeom uni = g;
+        const int talls[4] = {uni.seg_rows, (uni.seg_rows * 5 / 4 + 7) / 8 * 8, (uni.seg_rows * 3 / 2 + 7) / 8 * 8, uni.seg_rows * 2};
+        const int divs[5] = {2, 3, 4, 6, 8};
+        for (int ti = 0; ti < 4; ++ti) {
+            const int T = talls[ti] > H ? (H + 7) / 8 * 8 : talls[ti];
+            for (int di = 0; di < 5; ++di) {
+                const int sh = (T / divs[di] + 7) / 8 * 8;
+                if (sh < 16 || sh >= T) continue;
+                const int full = H / T;
+                for (int nt = (full > 3 ? full - 3 : 0); nt * T < H; ++nt) {
+                    const int nseg = geom_nseg(H, T, nt, sh);
+                    if ((long long)cols * nseg > 40000) continue;
+                    const double m = simulate_makespan(H, cols, T, nt, sh, extra);
+                    if (m < best * 0.985) { best = m; g.seg_rows = T; g.seg_short = sh; g.n_tall = nt; g.nseg = nseg; }
+                }
+            }
+        }
+    }
+    static const bool debug_geom = getenv("MMIF_DEBUG_GEOM") != nullptr;
+    if (debug_geom)
+        fprintf(stderr, "[mmif] bwd geometry B=%d H=%d W=%d win=%d: %d strips, %d segments = %d x %d rows + %d x %d rows\n", B, H, W, win,
+                g.nstrip, g.nseg, g.n_tall < g.nseg ? g.n_tall : g.nseg, g.seg_rows, g.nseg > g.n_tall ? g.nseg - g.n_tall : 0, g.seg_short);
+    Key& k = memo[memo_next];
+    k.B = B; k.H = H; k.W = W; k.win = win; k.g = g;
+    memo_next = (memo_next + 1) % 8;
+    if (memo_n < 8) ++memo_n;
     return g;
 }
 
@@ -44,7 +150,7 @@ struct BwdParams {
     const float* gout[3];    // upstream gradients of the three loss values (device scalars; all NULL = unit upstream;
                              // gout[0] set and gout[1] / gout[2] NULL = those two terms get no gradient)
     int B, H, W, Hout, Wout;
-    int seg_rows, nseg, nstrip;
+    int seg_rows, seg_short, n_tall, nseg, nstrip;   // row segments: see BwdGeom
     Taps taps;
     float C1, C2;
     int pixel_combine, grad_combine, pixel_norm, grad_norm;
@@ -103,11 +209,13 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemBwd& sb = *reinterpret_cast<SmemBwd*>(smem_raw);
     SmemB& sm = sb.s;
-    const int strip = blockIdx.x, seg = blockIdx.y, n = blockIdx.z;
-    const int j0 = strip * kTG, i0 = seg * p.seg_rows;
+    const int strip = blockIdx.x, n = blockIdx.y, seg = blockIdx.z;        // segment slowest: tall segments are dispatched first
+    const int j0 = strip * kTG;
+    const int i0 = (seg < p.n_tall) ? seg * p.seg_rows : p.n_tall * p.seg_rows + (seg - p.n_tall) * p.seg_short;
+    const int seg_h = (seg < p.n_tall) ? p.seg_rows : p.seg_short;
     const int jw0 = j0 - kOFF;             // first input column of the ring (multiple of 4); windows start at jw0 + kVOFF
     const int R0 = i0 - HALO;              // first window / input row of the segment
-    const int iend = min(i0 + p.seg_rows, p.H);
+    const int iend = min(i0 + seg_h, p.H);
     const int jend = min(j0 + kTG, p.W);
     const int nb = (iend - R0 + kRB - 1) / kRB;   // batch b emits gradient rows [R0+8b, R0+8b+8)
     const size_t img_off = (size_t)n * p.H * p.W;
@@ -552,7 +660,7 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.dF_unit = dF_unit;
     p.gout[0] = up.g[0]; p.gout[1] = up.g[1]; p.gout[2] = up.g[2];
     p.B = B; p.H = H; p.W = W; p.Hout = g.Hout; p.Wout = g.Wout;
-    p.seg_rows = g.seg_rows; p.nseg = g.nseg; p.nstrip = g.nstrip;
+    p.seg_rows = g.seg_rows; p.seg_short = g.seg_short; p.n_tall = g.n_tall; p.nseg = g.nseg; p.nstrip = g.nstrip;
     make_taps(&p.taps, win, (ex && ex->win) ? ex->sigma : 1.5);
     const double L = cfg->data_range;
     p.C1 = (float)((0.01 * L) * (0.01 * L)); p.C2 = (float)((0.03 * L) * (0.03 * L));
@@ -595,7 +703,7 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false, true>, at, sz));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false, true>, at, sz));
     }
-    dim3 grid(g.nstrip, g.nseg, B);
+    dim3 grid(g.nstrip, B, g.nseg);
     if (!zmode && dF_unit) {
         const size_t n = (size_t)B * H * W;
         const int vec = (((uintptr_t)dF | (uintptr_t)dF_unit) & 15) == 0;

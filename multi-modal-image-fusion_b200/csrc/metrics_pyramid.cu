@@ -424,8 +424,11 @@ static int run_vif(const float* a, const float* b, const float* f, int N, int H,
         memset(&L, 0, sizeof(L));
         L.win = k; L.sigma = (double)k / 5.0; L.epi = EPI_VIF; L.finalize = FIN_SUMS; L.data_range = 255.f;
         L.cfg.pixel_norm = L.cfg.grad_norm = MMIF_NORM_L1;
-        static const char* vif_eps = getenv("MMIF_VIF_EPS_EMULATION");      // experiment switch, see DESIGN.md section 2
-        L.plain_moments = (vif_eps && atoi(vif_eps) == 1) ? 0 : 1;
+        // Experiment switch: exact central moments instead of the emulation of the reference's fp32
+        // window (sum 1 + eps).  Measured: WITHOUT the emulation 26 parity cases fail (random 8-bit images by 5e-5..1e-4),
+        // with it only flat-region-dominated real images remain ill-conditioned — so the emulation stays on.
+        static const char* vif_plain = getenv("MMIF_VIF_PLAIN_MOMENTS");
+        L.plain_moments = (vif_plain && atoi(vif_plain) == 1) ? 1 : 0;
         int rc = launch_moment_fwd(L, ca, cb, cf, N, d.h[s], d.w[s], raw + s * 8, stride, nullptr, ws.fwd_ws, ws.fwd_ws_bytes, st);
         if (rc) return rc;
     }

@@ -126,3 +126,46 @@ def qabf_tie_allowance(a, b, f, L=1.5, tol=2e-6):
     gmax = torch.max(ga, gb)
     near = (gf - gmax).abs() <= tol * gmax.clamp(min=1e-30)
     return ((loss * near).sum() / (wa + wb).sum()).item()
+
+
+def viff_tie_allowance(a, b, f, noise=1e-6, gtol=1e-5):
+    """calc_viff(simple=False) (metric.py:461-491) takes, per pixel and scale, the (numerator, denominator) of the source with
+    the smaller gain: pick = g1 < g2, a HARD selection between two values that can differ a lot.  Where a local variance is
+    at the fp32 rounding floor of blur(x^2) - mu^2 (|s| <= noise * E[x^2]: saturated / flat patches — the reference's own
+    fp32 variance there is rounding noise around 0 that the `< 1e-10` rules of metric.py:436-452 then branch on) or the two
+    gains agree to gtol, the selection is decided by rounding in ANY fp32 evaluation; the reference's fp32 and fp64 per-scale
+    ratios differ by 1e-4..8e-4 on such images while their weighted sum happens to agree to 1e-5.  Returns the amount by
+    which the weighted VIFF can move if every such pixel flips (first-order bound), evaluated in float64."""
+    import torch
+    from oracle import fusion_metric as OM
+    from oracle.fusion_loss import blur
+    a, b, f = (torch.as_tensor(x, dtype=torch.float64) for x in (a, b, f))
+
+    def var_maps(ref, dist):
+        out, u, v = [], ref.clone(), dist.clone()
+        for scale in range(1, 5):
+            n = 2 ** (4 - scale + 1) + 1
+            w = OM.metric_window(n, n / 5).to(ref)
+            if scale > 1:
+                u, v = blur(u, w)[..., ::2, ::2], blur(v, w)[..., ::2, ::2]
+            mu_u, mu_v = blur(u, w), blur(v, w)
+            e1, e2 = blur(u * u, w), blur(v * v, w)
+            out.append((e1 - mu_u * mu_u, e2 - mu_v * mu_v, e1, e2))
+        return out
+
+    n1, d1, g1 = OM.vif_maps(a, f)
+    n2, d2, g2 = OM.vif_maps(b, f)
+    m1, m2 = var_maps(a, f), var_maps(b, f)
+    p = [1.0 / 2.15, 0.0, 0.15 / 2.15, 1.0 / 2.15]
+    total = 0.0
+    for k in range(4):
+        pick = g1[k] < g2[k]
+        num = torch.where(pick, n1[k], n2[k]).sum()
+        den = torch.where(pick, d1[k], d2[k]).sum()
+        s1a, s2f, e1a, e2f = m1[k]
+        s1b, _, e1b, _ = m2[k]
+        unc = (s1a <= noise * e1a) | (s1b <= noise * e1b) | (s2f <= noise * e2f) | \
+              ((g1[k] - g2[k]).abs() <= gtol * torch.maximum(g1[k].abs(), g2[k].abs()))
+        dn, dd = ((n1[k] - n2[k]).abs() * unc).sum(), ((d1[k] - d2[k]).abs() * unc).sum()
+        total += p[k] * (dn / den + num / den ** 2 * dd).item()
+    return total

@@ -29,15 +29,23 @@ def T(x):
     return torch.from_numpy(np.ascontiguousarray(x)).float()
 
 
+def _allowance(name, kind, metric):
+    """Tie allowances of the two metric families with a hard per-pixel selection (evaluated only if the plain gate fails)."""
+    if metric in ('nabf', 'labf'):
+        return lambda: gates.qabf_tie_allowance(*S.case(name, kind))
+    if metric == 'viff':
+        return lambda: gates.viff_tie_allowance(*S.case(name, kind))
+    return None
+
+
 @pytest.mark.parametrize('name,kind', CASES)
 def test_metric_row_cuda_inputs(name, kind):
     _, _, MM = _mods()
     a, b, f = (T(x).cuda() for x in S.case(name, kind))
     row = MM.eval_metrics_batch(a, b, f)[0].cpu().numpy()
     r32, r64 = SG[f'{name}/{kind}/f32/metrics'], SG[f'{name}/{kind}/f64/metrics']
-    tie = lambda: gates.qabf_tie_allowance(*S.case(name, kind))
     for k, nm in enumerate(OM.METRIC_NAMES):
-        gates.assert_scalar(f'{name}/{kind}/{nm}', row[k], r32[k], r64[k], allowance=tie if nm in ('nabf', 'labf') else None)
+        gates.assert_scalar(f'{name}/{kind}/{nm}', row[k], r32[k], r64[k], allowance=_allowance(name, kind, nm))
 
 
 @pytest.mark.parametrize('name,kind', CASES)
@@ -67,10 +75,9 @@ def test_eval_py_call_pattern_cpu_inputs(name):
     assert all(isinstance(v, torch.Tensor) and v.dim() == 0 and not v.is_cuda for v in vals)
     assert vals[9].dtype == torch.float64
     r32, r64 = SG[f'{name}/{kind}/f32/metrics'], SG[f'{name}/{kind}/f64/metrics']
-    tie = lambda: gates.qabf_tie_allowance(*S.case(name, kind))
     for k, nm in enumerate(OM.METRIC_NAMES):
         gates.assert_scalar(f'{name}/{kind}/{nm} (drop-in, cpu tensors)', vals[k].item(), r32[k], r64[k],
-                            allowance=tie if nm in ('nabf', 'labf') else None)
+                            allowance=_allowance(name, kind, nm))
 
 
 def _loss_case(name, kind):
