@@ -284,3 +284,42 @@ def test_kernel_names_seen_by_cupti():
                or ('fusion_loss_bwd_kernel' in n and '1, 1, 0' in n.replace('(bool)', '')) for n in names), names
     assert any('rescale_unit_kernel' in n for n in names), names
     assert not any('moment_fwd_kernel' in n for n in names), names
+
+
+def test_train_step_loss_captures_into_a_cuda_graph():
+    """The three module calls + total.backward() of train.py:64-71 are capturable (no host sync, no allocation outside the
+    graph's pool, no host-side decision that depends on device data): replaying the graph on new data gives the eager numbers."""
+    L, ML = _mods()
+    g = torch.Generator().manual_seed(21)
+    a0, b0, f0 = (torch.rand(4, 1, 96, 160, generator=g).cuda() for _ in range(3))
+    a1, b1, f1 = (torch.rand(4, 1, 96, 160, generator=g).cuda() for _ in range(3))
+    sa, sb = a0.clone(), b0.clone()
+    sf = f0.clone().requires_grad_(True)
+    mods = (ML.SSIMLoss('ssim', weight=1.0), ML.PixelLoss('l1', weight=0.01), ML.GradLoss('l1', weight=0.1))
+
+    def step(A, B_, F_):
+        tot = mods[0](A, B_, F_) + mods[1](A, B_, F_, mode='max') + mods[2](A, B_, F_, mode='max')
+        tot.backward()
+        return tot
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            sf.grad = None
+            step(sa, sb, sf)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    sf.grad = None
+    with torch.cuda.graph(graph):
+        stot = step(sa, sb, sf)
+    for A, B_, F_ in ((a1, b1, f1), (a0, b0, f0)):
+        sa.copy_(A); sb.copy_(B_)
+        with torch.no_grad():
+            sf.copy_(F_)
+        graph.replay()
+        torch.cuda.synchronize()
+        Fe = F_.clone().requires_grad_(True)
+        etot = step(A, B_, Fe)
+        assert stot.item() == etot.item()
+        assert torch.equal(sf.grad, Fe.grad)
