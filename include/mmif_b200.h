@@ -88,6 +88,7 @@ enum {
     MMIF_CNT_AUX = 7,              /* small operators: pad / halve / widen / norm / tv and their adjoints */
     MMIF_CNT_TMAP_ENCODE = 8,      /* cuTensorMapEncodeTiled calls (not a launch) */
     MMIF_CNT_TMAP_HIT = 9,         /* tensor maps served from the per-thread memo (not a launch) */
+    MMIF_CNT_TMAP_FAIL = 10,       /* encodings the driver refused although shape and alignment qualify (should stay 0) */
     MMIF_CNT_N = 16
 };
 /* out[i] = counter i for i < n (HOST memory). */

@@ -131,7 +131,7 @@ def launch_counts():
     buf = (ctypes.c_ulonglong * 16)()
     check(load().mmif_launch_counts(buf, 16))
     names = ('loss_fwd', 'loss_single_pass', 'loss_bwd', 'rescale', 'ssim_bwd_ext', 'moment_fwd', 'metric', 'aux',
-             'tmap_encode', 'tmap_hit')
+             'tmap_encode', 'tmap_hit', 'tmap_fail')
     return {n: int(buf[i]) for i, n in enumerate(names)}
 
 

@@ -116,10 +116,24 @@ bool make_tensor_map(CUtensorMap* map, const float* base, int N, int H, int W, i
     const cuuint64_t gstride[2] = {(cuuint64_t)W * 4ull, (cuuint64_t)W * (cuuint64_t)H * 4ull};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return false;
+    // cuTensorMapEncodeTiled is a DRIVER call and needs a current context; a thread that has not made a runtime call yet
+    // (autograd's backward thread on its first launch) has none -> CUDA_ERROR_INVALID_CONTEXT and a silent fall-back to the
+    // plain-load ring.  Bind the runtime's primary context of the current device to this thread first.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        int d = 0;
+        if (cudaGetDevice(&d) == cudaSuccess && cudaSetDevice(d) == cudaSuccess) (void)cudaFree(nullptr);
+        (void)cudaGetLastError();
+        ctx_bound = true;
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {          // belt and braces: bind and retry once
+        (void)cudaFree(nullptr);
+        r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { count_launch(MMIF_CNT_TMAP_FAIL); return false; }
     count_launch(MMIF_CNT_TMAP_ENCODE);
     MapMemo& m = t_maps[t_map_next];
     m.base = base; m.N = N; m.H = H; m.W = W; m.bw = box_w; m.bh = box_h;

@@ -24,6 +24,11 @@ REF_SRC = '/root/reference/core'
 OUT = os.path.join(HERE, '_ref', 'core')
 MODULES = ('fusion', 'block', 'model', 'loss', 'metric')       # import order: block needs fusion, model needs both
 PKG = 'mmif_reference_core'                                     # private package name: never collides with dropin/core
+# the reference's three scripts and what they import besides core/: byte-compiled too, so that the GPU box can run the
+# UNMODIFIED train.py / test.py / eval.py with dropin/ first on sys.path (tests/test_reference_scripts_gpu.py)
+REF_ROOT = '/root/reference'
+SCRIPTS_OUT = os.path.join(HERE, '_ref', 'scripts')
+SCRIPTS = ('train.py', 'test.py', 'eval.py', 'common.py', 'data/dataset.py', 'data/patches.py', 'data/transform.py')
 
 
 def build(force=False):
@@ -36,6 +41,12 @@ def build(force=False):
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             py_compile.compile(src, cfile=dst, dfile=f'reference/core/{m}.py', doraise=True, optimize=0,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    for rel in SCRIPTS:
+        src, dst = os.path.join(REF_ROOT, rel), os.path.join(SCRIPTS_OUT, rel + 'c')
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+            py_compile.compile(src, cfile=dst, dfile=f'reference/{rel}', doraise=True, optimize=0,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     with open(os.path.join(HERE, '_ref', 'BUILT_FROM'), 'w') as fh:
         fh.write(f'{REF_SRC} by oracle/build_ref.py with python {sys.version.split()[0]}\n')
     return available()
@@ -43,6 +54,25 @@ def build(force=False):
 
 def available():
     return all(os.path.exists(os.path.join(OUT, m + '.pyc')) for m in MODULES)
+
+
+def scripts_available():
+    return available() and all(os.path.exists(os.path.join(SCRIPTS_OUT, rel + 'c')) for rel in SCRIPTS)
+
+
+def stage_scripts(dst_repo, with_reference_loss=False):
+    """Lay the byte-compiled reference checkout out under `dst_repo` (train.pyc, test.pyc, eval.pyc, common.pyc, data/,
+    core/{model,block,fusion}.pyc) the way the scripts expect to find their neighbours.  core/loss and core/metric are
+    left out (they come from dropin/core, first on sys.path) unless `with_reference_loss` asks for the reference's own."""
+    import shutil
+    for rel in SCRIPTS:
+        d = os.path.join(dst_repo, rel + 'c')
+        os.makedirs(os.path.dirname(d), exist_ok=True)
+        shutil.copyfile(os.path.join(SCRIPTS_OUT, rel + 'c'), d)
+    os.makedirs(os.path.join(dst_repo, 'core'), exist_ok=True)
+    mods = MODULES if with_reference_loss else ('fusion', 'block', 'model')
+    for m in mods:
+        shutil.copyfile(os.path.join(OUT, m + '.pyc'), os.path.join(dst_repo, 'core', m + '.pyc'))
 
 
 def load():

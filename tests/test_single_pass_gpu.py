@@ -241,6 +241,7 @@ def test_modules_non_unit_unequal_and_retained_backward():
     g2, = torch.autograd.grad(total, F_)
     c1 = L.launch_counts()
     assert c1['loss_bwd'] - c0['loss_bwd'] >= 1, 'the second backward recomputes'
+    assert c1['tmap_fail'] == 0, 'a tensor-map encoding failed (autograd backward thread without a bound context?)'
     assert (g1 - g2).abs().max().item() <= 2e-6 * g2.abs().max().item()
     frac, mx, where = gates.grad_report(g2.cpu().numpy(), g64.sum(axis=0))
     assert frac <= 1e-4, (frac, mx, where)
