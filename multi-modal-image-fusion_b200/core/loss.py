@@ -128,6 +128,9 @@ class _FusedObjective(torch.autograd.Function):
         # The single-pass buffer is consumed by the first backward: it is rescaled IN PLACE (nothing to do at all for
         # the unit upstream of total.backward()) and handed to autograd; a second backward (retain_graph) recomputes.
         unit, ctx.dF_unit = ctx.dF_unit, None
+        tok = getattr(ctx, 'memo_token', None)
+        if tok is not None:
+            tok[0] = False          # this graph has been backpropagated: a later call on the same tensors builds a fresh one
         dF = unit if unit is not None else torch.empty_like(y)
         stream = L.stream_int(dev)
         ws = _loss_ws(lib, dev, stream, B, H, W)
@@ -143,7 +146,7 @@ class _Memo(threading.local):
     """One-entry memo PER THREAD so loss_fn1/2/3 called back to back (train.py:64-68) cost one launch."""
 
     def __init__(self):
-        self.key, self.refs, self.value, self.vec = None, None, None, None
+        self.key, self.refs, self.value, self.vec, self.token = None, None, None, None, None
         # what the sibling modules asked for last time: the guess for the next fused launch
         self.hint = {'pixel': ('max', 'l1'), 'grad': ('max', 'l1'), 'data_range': 1.0,
                      'w_ssim': 1.0, 'w_pixel': 0.01, 'w_grad': 0.1}
@@ -152,11 +155,16 @@ class _Memo(threading.local):
         want_grad = bool(SINGLE_PASS and imgf.requires_grad and torch.is_grad_enabled())    # the CALLER's grad mode
         key = (img1.data_ptr(), img1._version, img2.data_ptr(), img2._version, imgf.data_ptr(), imgf._version,
                imgf.shape, imgf.device, cfg_key, imgf.requires_grad and torch.is_grad_enabled(), want_grad)
-        if self.key == key and all(r() is t for r, t in zip(self.refs, (img1, img2, imgf))):
+        # a hit needs the same tensors (identity + version) AND a graph that has not been backpropagated yet: the reference
+        # builds a new graph on every call, so loss(...).backward() twice on the same tensors must keep working
+        if self.key == key and self.token[0] and all(r() is t for r, t in zip(self.refs, (img1, img2, imgf))):
             return self.value
         if img1.requires_grad or img2.requires_grad:
             raise NotImplementedError('gradients w.r.t. the source images are not built (train.py never needs them)')
         value = _FusedObjective.apply(img1, img2, imgf, cfg_key, want_grad)
+        self.token = [True]
+        if value[0].grad_fn is not None:
+            value[0].grad_fn.memo_token = self.token          # shared with the backward (which runs on autograd's thread)
         self.key, self.value = key, value
         self.refs = tuple(weakref.ref(t) for t in (img1, img2, imgf))
         return value

@@ -1,7 +1,8 @@
 """Recipe for ``oracle/_ref`` — the REAL reference as a built artefact that can travel to the GPU box.
 
 The reference is pure Python; "building" it means byte-compiling its own five ``core/`` modules from where they lie
-under /root/reference (never copied as sources) into ``oracle/_ref/core/*.pyc``.  ``oracle/_ref/`` is git-ignored (so
+under /root/reference (never copied as sources) into ``oracle/_ref/core/*.pyc.bin`` (bytecode under a neutral
+extension: the gpurun snapshot drops ``*.pyc`` files).  ``oracle/_ref/`` is git-ignored (so
 the history stays free of reference code) but not gpurun-ignored, so — like a compiled ``.so`` — it ships with the
 snapshot to the GPU box, where /root/reference does not exist.
 
@@ -23,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = '/root/reference/core'
 OUT = os.path.join(HERE, '_ref', 'core')
 MODULES = ('fusion', 'block', 'model', 'loss', 'metric')       # import order: block needs fusion, model needs both
+EXT = '.pyc.bin'                                                # python bytecode; '*.pyc' does not survive the gpurun snapshot
 PKG = 'mmif_reference_core'                                     # private package name: never collides with dropin/core
 # the reference's three scripts and what they import besides core/: byte-compiled too, so that the GPU box can run the
 # UNMODIFIED train.py / test.py / eval.py with dropin/ first on sys.path (tests/test_reference_scripts_gpu.py)
@@ -37,12 +39,12 @@ def build(force=False):
         return available()
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
-        src, dst = os.path.join(REF_SRC, m + '.py'), os.path.join(OUT, m + '.pyc')
+        src, dst = os.path.join(REF_SRC, m + '.py'), os.path.join(OUT, m + EXT)
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             py_compile.compile(src, cfile=dst, dfile=f'reference/core/{m}.py', doraise=True, optimize=0,
                                invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     for rel in SCRIPTS:
-        src, dst = os.path.join(REF_ROOT, rel), os.path.join(SCRIPTS_OUT, rel + 'c')
+        src, dst = os.path.join(REF_ROOT, rel), os.path.join(SCRIPTS_OUT, rel[:-3] + EXT)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             py_compile.compile(src, cfile=dst, dfile=f'reference/{rel}', doraise=True, optimize=0,
@@ -53,11 +55,11 @@ def build(force=False):
 
 
 def available():
-    return all(os.path.exists(os.path.join(OUT, m + '.pyc')) for m in MODULES)
+    return all(os.path.exists(os.path.join(OUT, m + EXT)) for m in MODULES)
 
 
 def scripts_available():
-    return available() and all(os.path.exists(os.path.join(SCRIPTS_OUT, rel + 'c')) for rel in SCRIPTS)
+    return available() and all(os.path.exists(os.path.join(SCRIPTS_OUT, rel[:-3] + EXT)) for rel in SCRIPTS)
 
 
 def stage_scripts(dst_repo, with_reference_loss=False):
@@ -68,11 +70,11 @@ def stage_scripts(dst_repo, with_reference_loss=False):
     for rel in SCRIPTS:
         d = os.path.join(dst_repo, rel + 'c')
         os.makedirs(os.path.dirname(d), exist_ok=True)
-        shutil.copyfile(os.path.join(SCRIPTS_OUT, rel + 'c'), d)
+        shutil.copyfile(os.path.join(SCRIPTS_OUT, rel[:-3] + EXT), d)
     os.makedirs(os.path.join(dst_repo, 'core'), exist_ok=True)
     mods = MODULES if with_reference_loss else ('fusion', 'block', 'model')
     for m in mods:
-        shutil.copyfile(os.path.join(OUT, m + '.pyc'), os.path.join(dst_repo, 'core', m + '.pyc'))
+        shutil.copyfile(os.path.join(OUT, m + EXT), os.path.join(dst_repo, 'core', m + '.pyc'))
 
 
 def load():
@@ -88,7 +90,7 @@ def load():
     sys.modules[PKG] = pkg
     for m in MODULES:
         name = f'{PKG}.{m}'
-        loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(OUT, m + '.pyc'))
+        loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(OUT, m + EXT))
         mspec = importlib.util.spec_from_loader(name, loader)
         mod = importlib.util.module_from_spec(mspec)
         sys.modules[name] = mod

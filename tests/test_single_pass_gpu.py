@@ -324,3 +324,18 @@ def test_train_step_loss_captures_into_a_cuda_graph():
         etot = step(A, B_, Fe)
         assert stot.item() == etot.item()
         assert torch.equal(sf.grad, Fe.grad)
+
+
+def test_calling_the_losses_twice_on_the_same_tensors_builds_two_graphs():
+    """The reference builds a new autograd graph on every call; the one-launch memo must not make a second
+    loss(...).backward() on the same tensors fail (or silently reuse a consumed graph)."""
+    L, ML = _mods()
+    a, b, f = (T(x).cuda() for x in cases.loss_case('rand_2x40x37'))
+    F_ = f.clone().requires_grad_(True)
+    sum(_three(ML, a, b, F_)).backward()
+    g1 = F_.grad.clone()
+    F_.grad = None
+    c0 = L.launch_counts()
+    sum(_three(ML, a, b, F_)).backward()            # same tensor objects, same versions
+    assert L.launch_counts()['loss_single_pass'] - c0['loss_single_pass'] == 1
+    assert torch.equal(F_.grad, g1)
