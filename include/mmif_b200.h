@@ -236,6 +236,12 @@ int mmif_hist(const float* a, const float* b, const float* f, int N, int H, int 
  * qabf, nabf (modified), labf, nabf_unmodified (calc_Nabf(modified=False), metric.py:273). */
 int mmif_qabf(const float* a, const float* b, const float* f, int N, int H, int W, float L,
               double* out, void* ws, size_t ws_bytes, void* stream);
+/* The same plus the raw sums behind the four ratios -> per pair 9 doubles: qabf, nabf, labf, nabf_unmodified,
+ * sum(Qaf wa + Qbf wb), sum(wa + wb), sum of the nabf terms, sum of the labf terms, sum of the unmodified-nabf terms.
+ * calc_Qabf on a batch (N > 1) is the ratio of the sums over all pairs (metric.py:233-256 sums over every dimension). */
+#define MMIF_QABF_RAW_DOUBLES 9
+int mmif_qabf_raw(const float* a, const float* b, const float* f, int N, int H, int W, float L,
+                  double* out, void* ws, size_t ws_bytes, void* stream);
 
 /* calc_ssim(x,f,win,data_range,use_padding,full=True) (metric.py:316-364) for the two pairs
  * (a,f) and (b,f) -> per pair 4 doubles: ssim_af, cs_af, ssim_bf, cs_bf (global means). */

@@ -15,7 +15,7 @@ SYMBOLS = [
     'mmif_loss_workspace_bytes', 'mmif_loss_out_doubles', 'mmif_fusion_loss_fwd', 'mmif_fusion_loss_bwd',
     'mmif_fusion_loss_bwd3', 'mmif_launch_counts',
     'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_ssim_fwd_win', 'mmif_ssim_bwd_ex_win', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
-    'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_ssim',
+    'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_qabf_raw', 'mmif_ssim',
     'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8', 'mmif_widen_u8_unit',
     'mmif_eval_suite_u8', 'mmif_eval_suite_u8_host', 'mmif_norm_workspace_bytes', 'mmif_norm_loss', 'mmif_norm_loss_bwd', 'mmif_test_post',
 ]
@@ -79,6 +79,7 @@ def load():
     lib.mmif_stats.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]
     lib.mmif_hist.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, sz, vp]
     lib.mmif_qabf.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, sz, vp]
+    lib.mmif_qabf_raw.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_ssim.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, ci, vp, vp, sz, vp]
     lib.mmif_msssim.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_viff.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, sz, vp]

@@ -11,6 +11,7 @@ benchmark use; the per-function drop-ins share kernel results through a small pe
 the 20-odd calls of ``eval_metrics`` (eval.py:29-75) cost one launch per kernel family.
 """
 import ctypes
+import math
 import weakref
 
 import torch
@@ -100,16 +101,94 @@ class _PairMemo:
 _memo = _PairMemo()
 
 
+def _combine_batch(kind, val, part, extra):
+    """Per-pair rows (n, K) -> ONE row (1, K) in the same layout holding what the reference's function returns for a batch:
+    every reference metric reduces over ALL dimensions, i.e. over the whole (N,1,H,W) batch as one population
+    (metric.py:25-491) — global means / variances / correlations, one histogram, ratios of batch-wide sums.  float64 torch
+    ops on the kernels' per-pair results (a few hundred scalars; the pixels were reduced by the kernels)."""
+    rows = val if part is None else val[part]
+    n = rows.shape[0] if rows is not None else 0
+    if kind == 'stats':
+        r = rows
+        mf, ma, mb = r[:, 0].mean(), r[:, 9].mean(), r[:, 10].mean()
+        e2 = lambda sd, m: (sd * sd + m * m).mean()                       # E[x^2] over the batch
+        vf, va, vb = e2(r[:, 1], r[:, 0]) - mf * mf, e2(r[:, 11], r[:, 9]) - ma * ma, e2(r[:, 12], r[:, 10]) - mb * mb
+        cov = lambda cc, s1, s2, m1, m2, g1, g2: (cc * s1 * s2 + m1 * m2).mean() - g1 * g2
+        caf = cov(r[:, 6], r[:, 11], r[:, 1], r[:, 9], r[:, 0], ma, mf)
+        cbf = cov(r[:, 7], r[:, 12], r[:, 1], r[:, 10], r[:, 0], mb, mf)
+        cab = cov(r[:, 13], r[:, 11], r[:, 12], r[:, 9], r[:, 10], ma, mb)
+        out = torch.zeros(1, L.ST_COUNT, dtype=torch.float64, device=r.device)
+        out[0, 0], out[0, 1], out[0, 2] = mf, vf.clamp(min=0).sqrt(), r[:, 2].mean()
+        out[0, 3] = (r[:, 3] * r[:, 3]).mean().sqrt()                      # sf^2 = mean dv^2 + mean dh^2 is additive over the batch
+        out[0, 4], out[0, 5] = r[:, 4].mean(), r[:, 5].mean()
+        out[0, 6], out[0, 7] = caf / (va * vf).sqrt(), cbf / (vb * vf).sqrt()
+        v_fa, v_fb = vf + va - 2.0 * caf, vf + vb - 2.0 * cbf             # scd = cc(f-a, b) + cc(f-b, a), metric.py:95-99
+        out[0, 8] = (cbf - cab) / (v_fa * vb).sqrt() + (caf - cab) / (v_fb * va).sqrt()
+        out[0, 9], out[0, 10], out[0, 11], out[0, 12] = ma, mb, va.clamp(min=0).sqrt(), vb.clamp(min=0).sqrt()
+        out[0, 13] = cab / (va * vb).sqrt()
+        return out
+    if kind == 'hist':                                                    # ONE histogram over the batch (metric.py:103-188)
+        c = val[0].to(torch.int64).sum(dim=0)
+        total = float(extra)                                              # pixels in the batch
+        ha, hb, hf = (c[k * 256:(k + 1) * 256].double() for k in range(3))
+        jaf, jbf = c[768:768 + 65536].double(), c[768 + 65536:].double()
+
+        def ent(h):
+            p = h[h > 0] / total
+            return -(p * torch.log2(p)).sum()
+
+        def cross(h1, h2):
+            m = (h1 > 0) & (h2 > 0)
+            return (h1[m] / total * torch.log2(h1[m] / h2[m])).sum()
+
+        ea, eb, ef, jea, jeb = ent(ha), ent(hb), ent(hf), ent(jaf), ent(jbf)
+        out = torch.zeros(1, L.EN_COUNT, dtype=torch.float64, device=c.device)
+        out[0, 0], out[0, 1], out[0, 2], out[0, 3], out[0, 4] = ea, eb, ef, jea, jeb
+        out[0, 5], out[0, 6] = cross(ha, hf), cross(hb, hf)
+        out[0, 7], out[0, 8] = ea + ef - jea, eb + ef - jeb
+        out[0, 9], out[0, 10] = 2.0 * out[0, 7] / (ea + ef), 2.0 * out[0, 8] / (eb + ef)
+        return out
+    if kind == 'qabf':                                                    # rows = mmif_qabf_raw: ratios of batch-wide sums
+        t = rows[:, 4:9].sum(dim=0)
+        return torch.stack([t[0] / t[1], t[2] / t[1], t[3] / t[1], t[4] / t[1]]).view(1, 4)
+    if kind == 'ssim':                                                    # global mean of the maps (metric.py:357-364)
+        return rows.mean(dim=0, keepdim=True)
+    if kind == 'msssim':                                                  # per-level global means, then the product (metric.py:368-402)
+        lv = rows[:, 2:22].view(n, 5, 4).mean(dim=0)                      # (5, [ssim_af, cs_af, ssim_bf, cs_bf])
+        wts = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float64, device=rows.device)
+        out = torch.zeros(1, L.MSSSIM_DOUBLES, dtype=torch.float64, device=rows.device)
+        for k, (cs_col, ss_col) in enumerate(((1, 0), (3, 2))):
+            v = torch.cat([lv[:4, cs_col], lv[4:, ss_col]]).clamp(min=1e-7)
+            out[0, k] = torch.prod(v ** wts)
+        out[0, 2:] = lv.reshape(-1)
+        return out
+    if kind == 'viff':                                                    # sums over the batch per scale (metric.py:461-491)
+        sc = rows[:, 2:26].view(n, 4, 6).sum(dim=0)                       # (4, [num1, den1, num2, den2, num_sel, den_sel])
+        p = torch.tensor([1.0, 0.0, 0.15, 1.0], dtype=torch.float64, device=rows.device) / 2.15
+        out = torch.zeros(1, L.VIFF_DOUBLES, dtype=torch.float64, device=rows.device)
+        out[0, 0] = (p * sc[:, 4] / sc[:, 5]).sum()
+        out[0, 1] = sc[:, 0].sum() / sc[:, 1].sum() + sc[:, 2].sum() / sc[:, 3].sum()
+        out[0, 2:] = sc.reshape(-1)
+        return out
+    raise L.MmifError(f'no batch rule for {kind}')
+
+
 def _rows(ent, home, part=None):
-    """The (n, K) float64 rows of a memo entry where the caller lives: the device tensor, or its single host copy."""
+    """The float64 row(s) of a memo entry where the caller lives: the device tensor, or its single host copy.  A batch
+    (N > 1) is first combined into the ONE row the reference's function returns for it (`_combine_batch`)."""
     val = ent[2] if part is None else ent[2][part]
-    if home.type != 'cpu':
-        return val if val.device == home else val.to(home)
+    n = (ent[2][1] if ent[0][0] == 'hist' else val).shape[0]
     if ent[3] is None:
         ent[3] = {}
-    if part not in ent[3]:
-        ent[3][part] = val.cpu()
-    return ent[3][part]
+    if n > 1:
+        if ('g', part) not in ent[3]:
+            ent[3][('g', part)] = _combine_batch(ent[0][0], ent[2], part, math.prod(ent[0][-1][2]))
+        val = ent[3][('g', part)]
+    if home.type != 'cpu':
+        return val if val.device == home else val.to(home)
+    if ('h', part) not in ent[3]:
+        ent[3][('h', part)] = val.cpu()
+    return ent[3][('h', part)]
 
 
 class _Triples:
@@ -224,7 +303,7 @@ def hist_raw(a, b, f):
 def _qabf(a, b, f, Lexp):
     def run():
         imgs, shape, _ = _prep(a, b, f)
-        return _call('mmif_qabf', imgs, shape, 4, ctypes.c_float(Lexp))
+        return _call('mmif_qabf_raw', imgs, shape, 9, ctypes.c_float(Lexp))
     _triples.add(a, b, f)
     return _memo.get('qabf', (a, b, f), float(Lexp), run)
 
@@ -292,17 +371,19 @@ def _msssim2(a, b, f, win_size, data_range, use_padding):
         n, h, w = shape
         wts = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], dtype=torch.float64, device=imgs[0].device)
         cur = [t.view(n, h, w) for t in imgs]
-        vals = []
+        vals, levels = [], []
         for lvl in range(5):
             hh, ww = cur[0].shape[-2:]
             r = _ssim_level(cur, (n, hh, ww), win_size, data_range, True)     # window = min(win, h, w) per level (metric.py:323-325)
             vals.append(torch.stack([r[:, 1], r[:, 3]], dim=1) if lvl < 4 else torch.stack([r[:, 0], r[:, 2]], dim=1))
+            levels.append(r)
             if lvl < 4:
                 cur = [_halve_dev(t) for t in cur]
         v = torch.stack(vals, dim=0).clamp(min=1e-7)       # (5, n, 2)
         ms = torch.prod(v ** wts.view(5, 1, 1), dim=0)
         out = torch.zeros(n, L.MSSSIM_DOUBLES, dtype=torch.float64, device=ms.device)
         out[:, 0], out[:, 1] = ms[:, 0], ms[:, 1]
+        out[:, 2:] = torch.stack(levels, dim=1).reshape(n, 20)          # per level ssim_af, cs_af, ssim_bf, cs_bf (mmif_msssim layout)
         return out
     return _memo.get('msssim', (a, b, f), (int(win_size), float(data_range), bool(use_padding)), run)
 
@@ -322,9 +403,9 @@ def _scalar(rows, idx, dtype=torch.float32):
 
 
 def _single(t, what):
-    if t.dim() == 4 and t.shape[0] != 1:
-        raise NotImplementedError(f'{what}: the drop-in functions take one image pair (N=1) like every reference caller; '
-                                  'use eval_metrics_batch for batches')
+    """Every reference metric reduces over the whole batch; N > 1 is served by the batched kernels + `_combine_batch`."""
+    if t.dim() not in (2, 3, 4):
+        raise L.MmifError(f'{what}: (N,1,H,W), (N,H,W) or (H,W) expected, got {tuple(t.shape)}')
 
 
 def _stat1(img, idx_f, idx_a, idx_b):
@@ -622,15 +703,16 @@ def eval_subset_batch(img1, img2, imgf, L_exp=1.5):
 
 def eval_metrics(img1, img2, imgf):
     """The dict eval.py:29-75 builds for one pair (python floats), through the fused suite entry."""
-    _single(img1, 'eval_metrics')
     imgs, shape, _ = _prep(img1, img2, imgf)
+    if shape[0] != 1:
+        raise L.MmifError('eval_metrics takes one pair; use eval_metrics_batch for N pairs')
     row = _call('mmif_eval_suite', imgs, shape, L.EVAL_METRICS)[0].tolist()
     return dict(zip(METRIC_NAMES, row))
 
 
 def histograms(img1, img2, imgf):
-    """Integer counts (hist_a, hist_b, hist_f, joint_af, joint_bf) of one pair, as int64 CPU tensors."""
-    _single(img1, 'histograms')
-    c = _hist(img1, img2, imgf)[2][0][0].to(torch.int64).cpu()
+    """Integer counts (hist_a, hist_b, hist_f, joint_af, joint_bf) as int64 CPU tensors; a batch is ONE population, as in
+    calc_prob / calc_joint_prob (metric.py:103-145)."""
+    c = _hist(img1, img2, imgf)[2][0].to(torch.int64).sum(dim=0).cpu()
     return (c[0:256], c[256:512], c[512:768], c[768:768 + 65536].view(256, 256),
             c[768 + 65536:].view(256, 256))

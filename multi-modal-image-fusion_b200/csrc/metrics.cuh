@@ -42,9 +42,9 @@ int launch_stats(const float* a, const float* b, const float* f, int N, int H, i
 int launch_hist(const float* a, const float* b, const float* f, int N, int H, int W, uint32_t* counts, double* ent,
                 long long estride, MetricWs& ws, cudaStream_t st);
 int launch_qabf(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out, long long ostride,
-                MetricWs& ws, cudaStream_t st);
+                MetricWs& ws, cudaStream_t st, int q_raw = 0);
 int launch_pixel_metrics(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out_s,
-                         long long sstride, double* out_q, long long qstride, MetricWs& ws, cudaStream_t st);
+                         long long sstride, double* out_q, long long qstride, MetricWs& ws, cudaStream_t st, int q_raw = 0);
 int launch_tv(const float* x, int N, int H, int W, int norm, float weight, double* out, MetricWs& ws, cudaStream_t st);
 int stats_rows_per_block(int N, int H);
 size_t hist_extra_words(int N);

@@ -473,6 +473,15 @@ extern "C" int mmif_qabf(const float* a, const float* b, const float* f, int N, 
     return launch_qabf(a, b, f, N, H, W, L, out, 4, w, (cudaStream_t)stream);
 }
 
+/* mmif_qabf plus the five raw sums it is made of (per pair 9 doubles). */
+extern "C" int mmif_qabf_raw(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out, void* ws,
+                         size_t ws_bytes, void* stream) {
+    int rc = check_imgs(a, b, f, N, H, W); if (rc) return rc;
+    if (!out) { set_error("null out"); return MMIF_E_NULL; }
+    MetricWs w; rc = carve_metric_ws(&w, ws, ws_bytes, N, H, W); if (rc) return rc;
+    return launch_qabf(a, b, f, N, H, W, L, out, MMIF_QABF_RAW_DOUBLES, w, (cudaStream_t)stream, 1);
+}
+
 extern "C" int mmif_ssim(const float* a, const float* b, const float* f, int N, int H, int W, int win_size, float data_range,
                          int use_padding, double* out, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_imgs(a, b, f, N, H, W); if (rc) return rc;

@@ -54,7 +54,7 @@ template <bool STATS, bool QABF>
 __global__ void __launch_bounds__(128)
 pixel_metrics_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ F, int H, int W, int rpb,
                      float Lexp, double* partial, unsigned* counters, double* out_s, long long sstride, double* out_q,
-                     long long qstride) {
+                     long long qstride, int q_raw) {
     constexpr int K = (STATS ? kStatK : 0) + (QABF ? kQK : 0);
     constexpr int QO = STATS ? kStatK : 0;
     __shared__ double red[K * 4];
@@ -179,6 +179,10 @@ pixel_metrics_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
     if (QABF) {
         double* o = out_q + (size_t)n * qstride;
         o[0] = t[QO + 0] / t[QO + 1]; o[1] = t[QO + 2] / t[QO + 1]; o[2] = t[QO + 3] / t[QO + 1]; o[3] = t[QO + 4] / t[QO + 1];
+        if (q_raw) {                     // the five raw sums as well: a batch is combined as sum / sum (metric.py:233-256 with N > 1)
+#pragma unroll
+            for (int i = 0; i < kQK; ++i) o[4 + i] = t[QO + i];
+        }
     }
 }
 
@@ -193,16 +197,16 @@ int stats_rows_per_block(int N, int H) {       // TVLoss
 }
 
 int launch_pixel_metrics(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out_s,
-                         long long sstride, double* out_q, long long qstride, MetricWs& ws, cudaStream_t st) {
+                         long long sstride, double* out_q, long long qstride, MetricWs& ws, cudaStream_t st, int q_raw) {
     if (H < 2 || W < 2) { set_error("stats / qabf: H and W must be >= 2"); return MMIF_E_SHAPE; }
     const int rpb = pixel_rows_per_block(N, H, W);
     dim3 grid(ceil_div(W, 128), ceil_div(H, rpb), N);
     if (out_s && out_q)
-        pixel_metrics_kernel<true, true><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride);
+        pixel_metrics_kernel<true, true><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride, q_raw);
     else if (out_s)
-        pixel_metrics_kernel<true, false><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride);
+        pixel_metrics_kernel<true, false><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride, q_raw);
     else
-        pixel_metrics_kernel<false, true><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride);
+        pixel_metrics_kernel<false, true><<<grid, 128, 0, st>>>(a, b, f, H, W, rpb, L, ws.partial, ws.counters, out_s, sstride, out_q, qstride, q_raw);
     mmif::count_launch(MMIF_CNT_METRIC);
     MMIF_CUDA(cudaGetLastError());
     return MMIF_OK;
@@ -212,8 +216,8 @@ int launch_stats(const float* a, const float* b, const float* f, int N, int H, i
     return launch_pixel_metrics(a, b, f, N, H, W, 1.5f, out, ostride, nullptr, 0, ws, st);
 }
 int launch_qabf(const float* a, const float* b, const float* f, int N, int H, int W, float L, double* out, long long ostride,
-                MetricWs& ws, cudaStream_t st) {
-    return launch_pixel_metrics(a, b, f, N, H, W, L, nullptr, 0, out, ostride, ws, st);
+                MetricWs& ws, cudaStream_t st, int q_raw) {
+    return launch_pixel_metrics(a, b, f, N, H, W, L, nullptr, 0, out, ostride, ws, st, q_raw);
 }
 
 // =============================================================================== histograms

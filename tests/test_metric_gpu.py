@@ -301,3 +301,43 @@ def test_eval_py_call_sequence_shares_launches_across_the_triple(where):
     # an in-place change of the fused image invalidates everything that was learned
     f.add_(1.0)
     assert abs(MM.calc_mse(a, f).item() - row[3]) > 0
+
+
+@pytest.mark.parametrize('where', ['cuda', 'cpu'])
+def test_batched_inputs_reduce_over_the_whole_batch(where):
+    """Every reference metric reduces over ALL dimensions (metric.py:25-491): for N > 1 the drop-in functions return the
+    statistic of the whole batch as one population — global std / cc / scd, one histogram, ratios of batch-wide sums, per-level
+    global means in MS-SSIM — not a mean of per-pair values."""
+    MM = _mods()
+    g = torch.Generator().manual_seed(77)
+    a = torch.randint(0, 256, (3, 1, 96, 120), generator=g).float()
+    b = torch.randint(0, 256, (3, 1, 96, 120), generator=g).float()
+    a[1] = (a[1] * 0.3 + 100).floor()            # different means / contrasts per pair: global != mean of per-pair
+    b[2] = (b[2] * 0.5).floor()
+    f = torch.floor((a + b) / 2)
+    A, B_, F_ = (t.cuda() for t in (a, b, f)) if where == 'cuda' else (a, b, f)
+    got = {'mean': MM.calc_mean(F_), 'sd': MM.calc_std(F_), 'ag': MM.calc_ag(F_), 'sf': MM.calc_sf(F_), 'mse': MM.calc_mse(A, F_),
+           'cc': MM.calc_cc(B_, F_), 'scd': MM.calc_scd(A, B_, F_), 'en': MM.calc_entropy(F_), 'ce': MM.calc_cross_ent(A, F_),
+           'mi': MM.calc_mul_info(B_, F_), 'nmi': MM.calc_mul_info(A, F_, normalized=True), 'ssim': MM.calc_ssim(A, F_),
+           'msssim': MM.calc_msssim(B_, F_), 'viff': MM.calc_viff(A, B_, F_, simple=False), 'viff_s': MM.calc_viff(A, B_, F_, simple=True)}
+    q, n, l = MM.calc_Qabf(A, B_, F_, L=1.5, full=True)
+    got.update(qabf=q, nabf=n, labf=l)
+
+    def ref(dt):
+        x, y, z = a.to(dt), b.to(dt), f.to(dt)
+        r = {'mean': OM.mean(z), 'sd': OM.std(z), 'ag': OM.avg_gradient(z), 'sf': OM.spatial_freq(z), 'mse': OM.mse(x, z),
+             'cc': OM.corrcoef(y, z), 'scd': OM.scd(x, y, z), 'en': OM.entropy(z), 'ce': OM.cross_entropy(x, z),
+             'mi': OM.mutual_info(y, z), 'nmi': OM.mutual_info(x, z, normalized=True), 'ssim': OM.ssim(x, z),
+             'msssim': OM.msssim(y, z), 'viff': OM.viff(x, y, z, simple=False), 'viff_s': OM.viff(x, y, z, simple=True)}
+        r['qabf'], r['nabf'], r['labf'] = OM.qabf(x, y, z, L=1.5, full=True)
+        return {k: float(v) for k, v in r.items()}
+
+    r32, r64 = ref(torch.float32), ref(torch.float64)
+    for k, v in got.items():
+        assert v.dim() == 0 and v.is_cuda == (where == 'cuda')
+        gates.assert_scalar(f'batched/{k}', v.item(), r32[k], r64[k])
+    # and it is NOT the mean of the per-pair values where the two differ
+    per_pair = np.mean([MM.calc_std(F_[i:i + 1]).item() for i in range(3)])
+    assert abs(per_pair - got['sd'].item()) > 1e-3 * got['sd'].item()
+    ha, hb, hf, jaf, jbf = MM.histograms(A, B_, F_)
+    assert int(hf.sum()) == f.numel() and np.array_equal(hf.numpy(), OM.hist_counts(f).to(torch.int64).numpy())
