@@ -39,9 +39,10 @@ static inline bool first_use_on_device(unsigned long long* mask) {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess) return true;
     const unsigned long long bit = 1ull << (d & 63);
-    if (*mask & bit) return false;
-    *mask |= bit;
-    return true;
+    // atomic test-and-set: two host threads racing on the first launch both see a consistent mask (a duplicate
+    // cudaFuncSetAttribute would be harmless, a torn read-modify-write of the mask would not be)
+    const unsigned long long prev = __atomic_fetch_or(mask, bit, __ATOMIC_ACQ_REL);
+    return (prev & bit) == 0ull;
 }
 
 constexpr int kMaxWin = 17;
