@@ -346,7 +346,7 @@ def main():
         sharded = metric_suite_sharded_leg(dev, world, rank, MM) if world > 1 else None
         if rank == 0:
             result['torch_cuda_eager'] = torch_eager_leg(dev, ML, value)
-            result['metric_suite'] = metric_suite_leg(dev, MM)
+            result['metric_suite'] = metric_suite_leg(dev, MM, world)
             if sharded is not None:
                 result['metric_suite']['sharded_by_pair'] = sharded
         if world == 1:
@@ -722,7 +722,7 @@ def eval_py_row(MM, a, b, f):
     return [v.item() for v in vals]
 
 
-def metric_suite_leg(dev, MM):
+def metric_suite_leg(dev, MM, world=1):
     """Second headline metric: full 16-metric suite, pairs/s (BASELINE configs[2] and configs[3] shapes).
     `pairs_per_s`: images resident in HBM (float32, as the reference's functions take them);
     `e2e_*`: through the public batched entry with HOST buffers, H2D of the images and D2H of the rows inside
@@ -798,18 +798,36 @@ def metric_suite_leg(dev, MM):
         torch.cuda.synchronize()
         upload_ms = (time.perf_counter() - t0) / len(host_pairs) * 1e3
         del ups
-        torch.set_num_threads(os.cpu_count() or 1)
-        t0 = time.perf_counter()
-        OM.eval_pair(ca, cb, cf_)
-        cpu_s = time.perf_counter() - t0
+        cpu_s = None
+        if world == 1:          # under torchrun the other ranks spin on the host cores: a CPU timing there is not a baseline
+            torch.set_num_threads(os.cpu_count() or 1)
+            try:                # the reference's own core/metric.py (oracle/_ref) when the artefact is present, else the oracle port
+                from oracle import build_ref
+                RM = build_ref.load()[1]
+
+                def cpu_row():
+                    m_ = (RM.calc_mse(ca, cf_) + RM.calc_mse(cb, cf_)) * 0.5
+                    RM.calc_Qabf(ca, cb, cf_, L=1.5, full=True)
+                    for v_ in (RM.calc_std(cf_), RM.calc_ag(cf_), RM.calc_sf(cf_), RM.calc_psnr(m_), RM.calc_cc(ca, cf_), RM.calc_cc(cb, cf_),
+                               RM.calc_scd(ca, cb, cf_), RM.calc_entropy(cf_), RM.calc_cross_ent(ca, cf_), RM.calc_cross_ent(cb, cf_),
+                               RM.calc_mul_info(ca, cf_, normalized=True), RM.calc_mul_info(cb, cf_, normalized=True), RM.calc_ssim(ca, cf_),
+                               RM.calc_ssim(cb, cf_), RM.calc_msssim(ca, cf_), RM.calc_msssim(cb, cf_), RM.calc_viff(ca, cb, cf_, simple=False)):
+                        v_.item()
+                cpu_kind = "the reference's own core/metric.py (oracle/_ref), eval.py:29-75 call sequence"
+            except ImportError:
+                cpu_row = lambda: OM.eval_pair(ca, cb, cf_)
+                cpu_kind = 'oracle port of eval.py:29-75'
+            t0 = time.perf_counter()
+            cpu_row()
+            cpu_s = time.perf_counter() - t0
         out[name] = {'pairs_per_s': n / (ms * 1e-3), 'ms_per_batch': ms, 'pairs': n,
                      'pairs_per_s_smooth_flat_images': n / (ms_nat * 1e-3),
                      'hbm_frac_87.6B_per_pixel': 87.6 * n * h * w / (ms * 1e-3) / 1e9 / peak,
                      'e2e_f32_host_pairs_per_s': n / (ms_f32 * 1e-3), 'e2e_u8_host_pairs_per_s': n / (ms_u8 * 1e-3),
                      'h2d_bytes_f32': 12 * n * h * w, 'h2d_bytes_u8': 3 * n * h * w, 'd2h_bytes': n * 16 * 8,
                      'eval_py_call_pattern_ms_per_pair': per_pair_ms, 'eval_py_upload_share_ms_per_pair': upload_ms,
-                     'cpu_reference_pairs_per_s': 1.0 / cpu_s, 'cpu_cores': torch.get_num_threads(),
-                     'cpu_sample': '1 pair, oracle port of eval.py:29-75, single run'}
+                     'cpu_reference_pairs_per_s': (1.0 / cpu_s) if cpu_s else None, 'cpu_cores': torch.get_num_threads() if cpu_s else None,
+                     'cpu_sample': ('1 pair, single run: ' + cpu_kind) if cpu_s else 'not timed under torchrun (N > 1)'}
         if ms_sub is not None:      # BASELINE configs[3]: MS-SSIM + VIFF + Qabf only (51.6 algorithmic B/px)
             out[name]['configs3_subset_msssim_viff_qabf'] = {
                 'pairs_per_s': n / (ms_sub * 1e-3), 'ms_per_batch': ms_sub,
