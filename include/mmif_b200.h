@@ -154,6 +154,23 @@ int mmif_ssim_bwd_ex_win(const float* i1, const float* i2, const float* f, int B
                          const float* gout1, const float* pair_w, int cs_only, float scale, float* dF,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* Generic calc_ssim of the loss module (loss.py:52-110) for ONE pair (x, y) and ANY window of 1..17 taps (odd or even; the
+ * taps of (win, sigma) as registered with mmif_set_gaussian_taps, else built by the library), with everything the
+ * reference's autograd provides.  Direct k x k evaluation in double: the slow, complete companion of the strip kernels.
+ *   fwd: per_sample3 = [B][3] doubles (mean ssim, cs, sigma) or NULL; map_* = [B][H-win+1][W-win+1] floats or NULL
+ *        (size_average=False).  ws: mmif_ssim_generic_workspace_bytes, zero-filled once (only needed with per_sample3).
+ *   bwd: upstream gradients of ssim / cs / sigma as [B] floats (maps == 0, the per-sample means) or as per-position maps
+ *        (maps != 0); any of the three may be NULL (= 0).  Writes d/dx and / or d/dy ([B][H][W] floats, either may be
+ *        NULL).  coef: mmif_ssim_generic_coef_doubles doubles of device scratch. */
+size_t mmif_ssim_generic_workspace_bytes(int B, int H, int W, int win);
+size_t mmif_ssim_generic_coef_doubles(int B, int H, int W, int win);
+int mmif_ssim_generic_fwd(const float* x, const float* y, int B, int H, int W, int win, double sigma, float data_range,
+                          double* per_sample3, float* map_ssim, float* map_cs, float* map_sigma,
+                          void* ws, size_t ws_bytes, void* stream);
+int mmif_ssim_generic_bwd(const float* x, const float* y, int B, int H, int W, int win, double sigma, float data_range,
+                          const float* g_ssim, const float* g_cs, const float* g_sigma, int maps, float* dx, float* dy,
+                          double* coef, void* stream);
+
 /* One window size (11, 9, 7, 5 or 3; sigma by the loss rule, loss.py:34) of MSW_SSIM.forward
  * (loss.py:226-237): out_sums8[8*n] = sum over window positions of gamma*ssim(I1,If) + (1-gamma)*ssim(I2,If),
  * gamma = sigma1/(sigma1+sigma2) per position.  mmif_mswssim_bwd: dF (+)= gout1[0] * scale *

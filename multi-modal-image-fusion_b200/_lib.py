@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, 'libmmif_b200.so')
 SYMBOLS = [
     'mmif_version', 'mmif_last_error', 'mmif_check_device', 'mmif_set_gaussian_taps',
     'mmif_loss_workspace_bytes', 'mmif_loss_out_doubles', 'mmif_fusion_loss_fwd', 'mmif_fusion_loss_bwd',
-    'mmif_fusion_loss_bwd3', 'mmif_launch_counts',
+    'mmif_fusion_loss_bwd3', 'mmif_launch_counts', 'mmif_ssim_generic_workspace_bytes', 'mmif_ssim_generic_coef_doubles',
+    'mmif_ssim_generic_fwd', 'mmif_ssim_generic_bwd',
     'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_ssim_fwd_win', 'mmif_ssim_bwd_ex_win', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
     'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_qabf_raw', 'mmif_ssim',
     'mmif_msssim', 'mmif_viff', 'mmif_eval_suite', 'mmif_eval_suite_host', 'mmif_ssim_maps', 'mmif_widen_u8', 'mmif_widen_u8_unit',
@@ -63,6 +64,12 @@ def load():
     lib.mmif_fusion_loss_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, sz, vp]
     lib.mmif_fusion_loss_bwd3.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, vp, vp, sz, vp]
     lib.mmif_launch_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ci]
+    lib.mmif_ssim_generic_workspace_bytes.restype = sz
+    lib.mmif_ssim_generic_workspace_bytes.argtypes = [ci, ci, ci, ci]
+    lib.mmif_ssim_generic_coef_doubles.restype = sz
+    lib.mmif_ssim_generic_coef_doubles.argtypes = [ci, ci, ci, ci]
+    lib.mmif_ssim_generic_fwd.argtypes = [vp, vp, ci, ci, ci, ci, ctypes.c_double, cf, vp, vp, vp, vp, vp, sz, vp]
+    lib.mmif_ssim_generic_bwd.argtypes = [vp, vp, ci, ci, ci, ci, ctypes.c_double, cf, vp, vp, vp, ci, vp, vp, vp, vp]
     lib.mmif_tv_loss.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, sz, vp]
     lib.mmif_tv_loss_bwd.argtypes = [vp, ci, ci, ci, ci, cf, vp, vp, vp]
     lib.mmif_ssim_bwd_ex.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp, vp, ci, cf, vp, vp, sz, vp]
@@ -201,6 +208,18 @@ def set_window_taps(win, sigma, taps):
     if t.numel() != win:
         raise MmifError(f'expected {win} taps, got {t.numel()}')
     check(_lib.mmif_set_gaussian_taps(int(win), float(sigma), t.data_ptr()))
+
+
+_registered_taps = set()
+
+
+def ensure_window_taps(win, sigma):
+    """Register the reference's own taps of (win, sigma) once (any window size the loss module is asked for)."""
+    key = (int(win), float(sigma))
+    if key not in _registered_taps:
+        from ._windows import gauss_1d
+        set_window_taps(win, sigma, gauss_1d(win, sigma))
+        _registered_taps.add(key)
 
 
 def register_reference_taps():

@@ -11,10 +11,11 @@ Built on the same kernels: 'w-ssim' (per-sample gamma weights in the backward ke
 (one SSIM forward/backward launch per pyramid level + pooling adjoints), use_padding=True (reflect-pad
 operator + its adjoint, applied per pyramid level / per window for 'ms-ssim' / 'msw-ssim'), size_average=False
 (SSIM / CS / sigma maps), data_range=None auto-detect, TVLoss and NormLoss forward/backward, SSIM(win_size) for the
-windows 11/9/7/5/3 with a dict that is differentiable w.r.t. both images ('ssim' and 'cs' entries).  'msw-ssim' runs the
-same forward / backward kernels with the 11/9/7/5/3 windows and per-position weights.  Not built (raise
-NotImplementedError, never a silent fallback): gradients of the fused objective w.r.t. the sources, the gradient of the
-dict's 'sigma' entry w.r.t. img1, gradients through the size_average=False maps, even or > 11-tap SSIM windows.
+windows 11/9/7/5/3 on the strip kernels and for ANY other window of 2..17 taps (odd or even) on the generic kernels
+(mmif_ssim_generic_*), with a dict that is differentiable w.r.t. both images through all three entries, per-sample or as
+size_average=False maps.  'msw-ssim' runs the same forward / backward kernels with the 11/9/7/5/3 windows and per-position
+weights.  Not built (raise NotImplementedError, never a silent fallback): gradients of the fused objective w.r.t. the
+sources, SSIM windows above 17 taps, MSW_SSIM(size_average=True), MS_SSIM(size_average=False).
 """
 import ctypes
 import threading
@@ -227,6 +228,8 @@ def _fwd_per_sample(x1, x2, y, data_range, win=11):
     lib = L.load()
     B, H, W = y.shape
     dev = y.device
+    if win not in SSIM_WINDOWS or min(H, W) < 11:   # any other window / an image under 11 pixels: the generic kernels, one pair at a time
+        return torch.cat([_generic_fwd(x1, y, data_range, win), _generic_fwd(x2, y, data_range, win)], dim=1)
     out = torch.empty(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device=dev)
     nws = lib.mmif_loss_workspace_bytes(B, H, W)
     if nws == 0:
@@ -241,6 +244,15 @@ def _ssim_bwd_ex(x1, x2, y, data_range, gout1, pair_w, cs_only, scale, win=11):
     lib = L.load()
     B, H, W = y.shape
     dev = y.device
+    if win not in SSIM_WINDOWS or min(H, W) < 11:   # generic kernels: per-sample upstream (of the window MEAN) = gout1 * scale * pair weight
+        dF = None
+        for k, src in enumerate((x1, x2)):
+            g = (gout1.to(torch.float32).reshape(1) * float(scale)).expand(B)
+            if pair_w is not None:
+                g = g * pair_w[:, k].to(torch.float32)
+            _, d = _generic_bwd(src, y, data_range, win, None if cs_only else g, g if cs_only else None, None, False, False, True)
+            dF = d if dF is None else dF.add_(d)
+        return dF
     dF = torch.empty_like(y)
     ws = L.workspace(dev, lib.mmif_loss_workspace_bytes(B, H, W), 'loss', (B, H, W))
     pw = pair_w.to(torch.float32).contiguous() if pair_w is not None else None
@@ -285,6 +297,80 @@ class _WeightedSSIM(torch.autograd.Function):
         g1 = g.to(torch.float32).reshape(1).contiguous()
         dF = _ssim_bwd_ex(x1, x2, y, ctx.data_range, g1, pw, 0, 1.0 / y.shape[0])
         return None, None, dF.view(ctx.in_shape), None
+
+
+def _loss_sigma(win):
+    return 1.5 if win == 11 else 0.15 * (win - 1)        # loss.py:34
+
+
+def _generic_fwd(x, y, data_range, win, want_maps=False):
+    """mmif_ssim_generic_fwd on (B,H,W) device tensors -> (B,3) float64 per-sample [ssim, cs, sigma], or the three maps."""
+    lib = L.load()
+    B, H, W = y.shape
+    dev = y.device
+    sigma = _loss_sigma(win)
+    L.ensure_window_taps(win, sigma)
+    if want_maps:
+        maps = [torch.empty(B, 1, H - win + 1, W - win + 1, dtype=torch.float32, device=dev) for _ in range(3)]
+        L.call(dev, lib.mmif_ssim_generic_fwd, x.data_ptr(), y.data_ptr(), B, H, W, int(win), float(sigma), float(data_range), None,
+               maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, 0, L.stream_int(dev))
+        return maps
+    per = torch.empty(B, 3, dtype=torch.float64, device=dev)
+    ws = L.workspace(dev, lib.mmif_ssim_generic_workspace_bytes(B, H, W, int(win)), 'ssim_generic', (B, H, W, int(win)))
+    L.call(dev, lib.mmif_ssim_generic_fwd, x.data_ptr(), y.data_ptr(), B, H, W, int(win), float(sigma), float(data_range), per.data_ptr(),
+           None, None, None, ws.data_ptr(), ws.numel(), L.stream_int(dev))
+    return per
+
+
+def _generic_bwd(x, y, data_range, win, g_ssim, g_cs, g_sigma, maps, want_dx, want_dy):
+    """mmif_ssim_generic_bwd: upstream gradients (per-sample (B,) or per-position maps, any may be None) -> (dx, dy)."""
+    lib = L.load()
+    B, H, W = y.shape
+    dev = y.device
+    sigma = _loss_sigma(win)
+    L.ensure_window_taps(win, sigma)
+    gs = [None if g is None else g.to(device=dev, dtype=torch.float32).contiguous() for g in (g_ssim, g_cs, g_sigma)]
+    coef = torch.empty(lib.mmif_ssim_generic_coef_doubles(B, H, W, int(win)), dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x) if want_dx else None
+    dy = torch.empty_like(y) if want_dy else None
+    L.call(dev, lib.mmif_ssim_generic_bwd, x.data_ptr(), y.data_ptr(), B, H, W, int(win), float(sigma), float(data_range),
+           *(None if g is None else g.data_ptr() for g in gs), 1 if maps else 0, dx.data_ptr() if want_dx else None,
+           dy.data_ptr() if want_dy else None, coef.data_ptr(), L.stream_int(dev))
+    return dx, dy
+
+
+class _SSIMGeneric(torch.autograd.Function):
+    """calc_ssim of the loss module (loss.py:52-110) for ANY window size and either output form, differentiable w.r.t. both
+    images and through all three entries — the complete, slower path (direct k x k evaluation) behind SSIM(win_size=...)
+    for windows other than 11/9/7/5/3, for images smaller than the window (the reference shrinks the window to
+    min(win, H, W), loss.py:67-71), and for gradients through the size_average=False maps."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, data_range, win, size_average):
+        x, B, H, W = L.as_f32_3d(img1.detach(), 'img1')
+        y, _, _, _ = L.as_f32_3d(img2.detach(), 'img2')
+        if y.shape != x.shape:
+            raise L.MmifError(f'shape mismatch: {tuple(img1.shape)} {tuple(img2.shape)}')
+        L.ensure_device(x.device)
+        x, y = x.view(B, H, W), y.view(B, H, W)
+        k = min(int(win), H, W)                                    # loss.py:67-71
+        ctx.save_for_backward(x, y)
+        ctx.meta = (data_range, k, bool(size_average), img1.shape, img2.shape)
+        ctx.set_materialize_grads(False)
+        if size_average:
+            per = _generic_fwd(x, y, data_range, k).to(torch.float32)
+            return per[:, 0].contiguous(), per[:, 1].contiguous(), per[:, 2].contiguous()
+        return tuple(_generic_fwd(x, y, data_range, k, want_maps=True))
+
+    @staticmethod
+    def backward(ctx, g_ssim, g_cs, g_sigma):
+        x, y = ctx.saved_tensors
+        data_range, k, size_average, s1, s2 = ctx.meta
+        if g_ssim is None and g_cs is None and g_sigma is None:
+            return None, None, None, None, None
+        dx, dy = _generic_bwd(x, y, data_range, k, g_ssim, g_cs, g_sigma, not size_average, ctx.needs_input_grad[0],
+                              ctx.needs_input_grad[1])
+        return (dx.view(s1) if dx is not None else None), (dy.view(s2) if dy is not None else None), None, None, None
 
 
 class _PlainSSIM(torch.autograd.Function):
@@ -347,9 +433,11 @@ class _SSIMDict(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g2 = wrt(x, y).view(ctx.shape2)
         if ctx.needs_input_grad[0]:
-            if g_sigma is not None:
-                raise NotImplementedError("gradient of SSIM.forward()['sigma'] w.r.t. img1 is not built")
-            g1 = wrt(y, x).view(ctx.shape1)
+            g1 = wrt(y, x) if (g_ssim is not None or g_cs is not None) else None
+            if g_sigma is not None:             # sigma = clamp(var(img1), 1e-4) depends on img1 only: the generic backward
+                ds, _ = _generic_bwd(x, y, ctx.data_range, ctx.win, None, None, g_sigma.reshape(-1), False, True, False)
+                g1 = ds if g1 is None else g1.add_(ds)
+            g1 = g1.view(ctx.shape1) if g1 is not None else None
         return g1, g2, None, None
 
 
@@ -572,19 +660,26 @@ def _auto_range(img):
 def _ssim_dict(img1, img2, data_range, use_padding, size_average, win_size=11):
     """calc_ssim of the loss module with the module's own window (loss.py:52-110, 163-185): 11 taps, or 9 / 7 / 5 / 3
     (sigma by loss.py:34) for SSIM(win_size=...)."""
-    if win_size not in SSIM_WINDOWS:
-        raise NotImplementedError(f'SSIM windows {SSIM_WINDOWS} are built, not {win_size}')
     if use_padding:
         img1, img2 = _ReflectPad.apply(img1, win_size // 2), _ReflectPad.apply(img2, win_size // 2)
         use_padding = False
     if data_range is None:
         data_range = _auto_range(img1)
     needs_grad = torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad)
+    h, w = img1.shape[-2:]
+    fast_window = win_size in SSIM_WINDOWS and min(h, w) >= 11             # the strip kernels: their windows, images of 11+ pixels
+    if not fast_window or (not size_average and (needs_grad or win_size != 11)):
+        # any other window size (odd or even, up to 17 taps), an image smaller than the window (the reference shrinks the
+        # window, loss.py:67-71), or maps that must carry gradients: the generic kernels
+        if min(h, w) < int(win_size):
+            raise RuntimeError(f'image {(h, w)} smaller than the {win_size}-tap window of the module (conv2d fails in the reference too)')
+        if not 2 <= int(win_size) <= 17:
+            raise NotImplementedError('SSIM windows of 2..17 taps are built')
+        for t, nm in ((img1, 'img1'), (img2, 'img2')):
+            L.require_cuda(t, nm)
+        ss, cs, sg = _SSIMGeneric.apply(img1, img2, data_range, int(win_size), bool(size_average))
+        return {'ssim': ss, 'cs': cs, 'sigma': sg}
     if not size_average:
-        if win_size != 11:
-            raise NotImplementedError('SSIM maps (size_average=False) are built for the 11-tap window')
-        if needs_grad:
-            raise NotImplementedError('gradients through the SSIM maps (size_average=False) are not built')
         return ssim_maps(img1, img2, data_range)
     if needs_grad or win_size != 11:
         for t, nm in ((img1, 'img1'), (img2, 'img2')):
@@ -618,6 +713,43 @@ def ssim_maps(img1, img2, data_range):
     return {'ssim': maps[0], 'cs': maps[1], 'sigma': maps[2]}
 
 
+def _window_taps(win_size, window, h, w):
+    """The window size calc_ssim / calc_msssim end up with: min(win_size, h, w) when no window is passed (loss.py:67-71,
+    128-132), else the size of the passed window, which must be one create_window builds (loss.py:33-39)."""
+    if window is None:
+        return min(int(win_size), int(h), int(w))
+    k = int(window.shape[-1])
+    from .._windows import loss_window
+    if tuple(window.shape[-2:]) != (k, k) or not torch.equal(window.detach().reshape(k, k).float().cpu(), loss_window(k).reshape(k, k)):
+        raise NotImplementedError('only the Gaussian windows of create_window (loss.py:33-39) are built')
+    return k
+
+
+def create_window(win_size):
+    """reference loss.py:33-39"""
+    from .._windows import loss_window
+    return loss_window(win_size)
+
+
+def calc_ssim(img1, img2, win_size=11, window=None, data_range=None, use_padding=False, size_average=True):
+    """reference loss.py:52-110 (the function form: without a window it is built for min(win_size, h, w))."""
+    h, w = img1.shape[-2:]
+    return _ssim_dict(img1, img2, data_range, use_padding, size_average, _window_taps(win_size, window, h, w))
+
+
+def calc_msssim(img1, img2, win_size=11, window=None, weights=None, data_range=None, use_padding=False, size_average=True):
+    """reference loss.py:113-160 with its default five level weights."""
+    if weights is not None and not torch.allclose(weights.detach().float().cpu(), torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333])):
+        raise NotImplementedError('calc_msssim: the default level weights are built')
+    if not size_average:
+        raise NotImplementedError('size_average=False is not built yet')
+    h, w = img1.shape[-2:]
+    k = _window_taps(win_size, window, h, w)
+    if not 2 <= k <= 17:
+        raise NotImplementedError('SSIM windows of 2..17 taps are built')
+    return _MSSSIM.apply(img1, img1, img2, data_range, bool(use_padding), k)[0]
+
+
 class SSIM(nn.Module):
     '''Structural Similarity Index (reference loss.py:163-185)'''
 
@@ -642,8 +774,8 @@ class MS_SSIM(SSIM):
         self.register_buffer('weights', torch.FloatTensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333]))
 
     def forward(self, img1, img2):
-        if self.win_size not in SSIM_WINDOWS:
-            raise NotImplementedError(f'SSIM windows {SSIM_WINDOWS} are built, not {self.win_size}')
+        if not 1 < int(self.win_size) <= 17:
+            raise NotImplementedError('SSIM windows of 2..17 taps are built')
         if not self.size_average:
             raise NotImplementedError('size_average=False is not built yet')
         return _MSSSIM.apply(img1, img1, img2, self.data_range, bool(self.use_padding), int(self.win_size))[0]

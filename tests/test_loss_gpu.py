@@ -132,7 +132,7 @@ def test_errors_match_reference():
         ML.PixelLoss('l3')(x, x, x, mode='max')
     assert ML.PixelLoss('l1')(x, x, x, mode='other') is None
     with pytest.raises(NotImplementedError):
-        ML.SSIM(win_size=8)(x, x)                        # windows 11, 9, 7, 5, 3 are built
+        ML.SSIM(win_size=19)(x, x)                       # windows of 2..17 taps are built
     with pytest.raises(NotImplementedError):
         ML.SSIMLoss('ssim')(x.clone().requires_grad_(True), x, x)   # gradients w.r.t. the sources
     with pytest.raises(Exception):
@@ -342,10 +342,14 @@ def test_ssim_module_dict_is_differentiable(use_padding):
         frac, mx, where = gates.grad_report(got.cpu().numpy(), r64.numpy())
         ref_err = np.abs(q32.numpy() - r64.numpy()).max() / np.abs(r64.numpy()).max()
         assert mx <= max(1e-5, ref_err), f'{nm}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
-    # the clamped variance of img1 is not differentiable here w.r.t. img1: loud, not silent
+    # 'sigma' = clamp(var(img1), 1e-4) depends on img1 only: its gradient comes from the generic backward
+    w3 = torch.tensor([0.3, 1.1, -0.9])
     d = ML.SSIM(11, 1.0).cuda()(A, F_)
-    with pytest.raises(NotImplementedError):
-        d['sigma'].sum().backward()
+    gA, = torch.autograd.grad((w3.cuda() * d['sigma']).sum() + (w1.cuda() * d['ssim']).sum(), (A,))
+    o = OL.ssim(a64, f64, 11, None, 1.0, False)
+    rA, = torch.autograd.grad((w3.double() * o['sigma']).sum() + (w1.double() * o['ssim']).sum(), (a64,))
+    frac, mx, where = gates.grad_report(gA.cpu().numpy(), rA.numpy())
+    assert mx <= 1e-5, f"d(sigma + ssim)/d img1: max-norm err {mx:.3e} at {where}"
 
 
 @pytest.mark.parametrize('win', [9, 7, 5, 3])
@@ -384,8 +388,6 @@ def test_ssim_module_other_window_sizes(win, use_padding):
         # gate: 1e-5 of max|g|, or (3-tap window, sigma 0.3: nearly a delta, tiny variances) 1.5x the band the reference's
         # own fp32 graph keeps around the fp64 gradient — the same rule tests/gates.py applies to scalars
         assert mx <= max(1e-5, 1.5 * ref_err), f'win {win} {nm}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
-    with pytest.raises(NotImplementedError):
-        ML.SSIM(8, 1.0).cuda()(a.cuda(), f.cuda())
 
 
 @pytest.mark.parametrize('win,use_padding', [(7, False), (5, True)])
@@ -465,3 +467,127 @@ def _train_step_cases(ML, make, a, b):
         opt = torch.optim.Adam(net32.parameters(), lr=1e-4)
         torch.nn.utils.clip_grad_norm_(net32.parameters(), 5.0)
         opt.step()
+
+
+def _dict_obj(d, ws):
+    return sum((w.to(d[k]) * d[k]).sum() for k, w in zip(('ssim', 'cs', 'sigma'), ws))
+
+
+@pytest.mark.parametrize('win', [13, 8, 4, 2, 17])
+@pytest.mark.parametrize('use_padding', [False, True])
+def test_ssim_module_any_window_size(win, use_padding):
+    """SSIM(win_size) for windows the strip kernels are not instantiated for (odd or even, up to 17 taps; loss.py:33-39
+    builds any size): the generic kernels (mmif_ssim_generic_fwd / _bwd).  Dict against the oracle (fp32 band around fp64),
+    gradients of ALL THREE entries w.r.t. BOTH images against the fp64 oracle's autograd."""
+    ML = _mods()
+    a, _, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    ws = (torch.tensor([0.7, -1.3, 2.0]), torch.tensor([1.5, 0.25, -0.5]), torch.tensor([0.4, 0.9, -1.1]))
+    mod = ML.SSIM(win, 1.0, use_padding).cuda()
+    assert tuple(mod.window.shape) == (1, 1, win, win)
+    with torch.no_grad():
+        d0 = mod(a.cuda(), f.cuda())
+    o32, o64 = OL.ssim(a, f, win, None, 1.0, use_padding), OL.ssim(a.double(), f.double(), win, None, 1.0, use_padding)
+    for key in ('ssim', 'cs', 'sigma'):
+        for n in range(3):
+            gates.assert_scalar(f'win{win}/{key}[{n}]', d0[key][n].item(), o32[key][n].item(), o64[key][n].item())
+    A, F_ = a.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+    gA, gF = torch.autograd.grad(_dict_obj(mod(A, F_), ws), (A, F_))
+    a64, f64 = a.double().requires_grad_(True), f.double().requires_grad_(True)
+    rA, rF = torch.autograd.grad(_dict_obj(OL.ssim(a64, f64, win, None, 1.0, use_padding), ws), (a64, f64))
+    a32, f32 = a.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    qA, qF = torch.autograd.grad(_dict_obj(OL.ssim(a32, f32, win, None, 1.0, use_padding), ws), (a32, f32))
+    for nm, got, r64, q32 in (('d/d img1', gA, rA, qA), ('d/d img2', gF, rF, qF)):
+        frac, mx, where = gates.grad_report(got.cpu().numpy(), r64.numpy())
+        ref_err = np.abs(q32.numpy() - r64.numpy()).max() / np.abs(r64.numpy()).max()
+        assert mx <= max(1e-5, ref_err), f'win {win} {nm}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+    with pytest.raises(NotImplementedError):
+        ML.SSIM(19, 1.0).cuda()(a.cuda(), f.cuda())
+
+
+@pytest.mark.parametrize('win', [11, 6])
+def test_ssim_maps_carry_gradients(win):
+    """size_average=False (loss.py:99-108): per-position maps, differentiable w.r.t. both images (the reference's autograd
+    gives this for free; here the generic backward with per-position upstream gradients)."""
+    ML = _mods()
+    a, _, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+    g = torch.Generator().manual_seed(5)
+    Ho, Wo = a.shape[-2] - win + 1, a.shape[-1] - win + 1
+    wm = [torch.randn(3, 1, Ho, Wo, generator=g) for _ in range(3)]
+    mod = ML.SSIM(win, 1.0, False, size_average=False).cuda()
+    A, F_ = a.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+    d = mod(A, F_)
+    o64 = OL.ssim(a.double(), f.double(), win, None, 1.0, False, size_average=False)
+    o32 = OL.ssim(a, f, win, None, 1.0, False, size_average=False)
+    for key in ('ssim', 'cs', 'sigma'):
+        assert tuple(d[key].shape) == (3, 1, Ho, Wo)
+        err = (d[key].detach().cpu().double() - o64[key]).abs().max().item()
+        ref = (o32[key].double() - o64[key]).abs().max().item()
+        assert err <= max(1e-5 * o64[key].abs().max().item() + 1e-7, ref), f'{key} map: {err:.3e} (fp32 reference {ref:.3e})'
+    gA, gF = torch.autograd.grad(_dict_obj(d, wm), (A, F_))
+    a64, f64 = a.double().requires_grad_(True), f.double().requires_grad_(True)
+    rA, rF = torch.autograd.grad(_dict_obj(OL.ssim(a64, f64, win, None, 1.0, False, size_average=False), wm), (a64, f64))
+    a32, f32 = a.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    qA, qF = torch.autograd.grad(_dict_obj(OL.ssim(a32, f32, win, None, 1.0, False, size_average=False), wm), (a32, f32))
+    for nm, got, r64, q32 in (('d/d img1', gA, rA, qA), ('d/d img2', gF, rF, qF)):
+        frac, mx, where = gates.grad_report(got.cpu().numpy(), r64.numpy())
+        ref_err = np.abs(q32.numpy() - r64.numpy()).max() / np.abs(r64.numpy()).max()
+        assert mx <= max(1e-5, ref_err), f'{nm}: max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+
+
+def test_calc_ssim_function_form_shrinks_the_window():
+    """calc_ssim / calc_msssim called as functions (loss.py:52-160): without a window the reference builds one of
+    min(win_size, h, w) taps — a 7 x 40 image gets a 7-tap window (sigma 0.9) — and a passed create_window() is honoured."""
+    ML = _mods()
+    g = torch.Generator().manual_seed(9)
+    a, f = torch.rand(2, 1, 7, 40, generator=g), torch.rand(2, 1, 7, 40, generator=g)
+    d = ML.calc_ssim(a.cuda(), f.cuda(), data_range=1.0)
+    o32, o64 = OL.ssim(a, f, 11, None, 1.0), OL.ssim(a.double(), f.double(), 11, None, 1.0)
+    for key in ('ssim', 'cs', 'sigma'):
+        for n in range(2):
+            gates.assert_scalar(f'shrunk/{key}[{n}]', d[key][n].item(), o32[key][n].item(), o64[key][n].item())
+    a, f = torch.rand(2, 1, 6, 40, generator=g), torch.rand(2, 1, 6, 40, generator=g)      # even shrunk window: 6 taps
+    d = ML.calc_ssim(a.cuda(), f.cuda(), data_range=1.0)
+    o32, o64 = OL.ssim(a, f, 11, None, 1.0), OL.ssim(a.double(), f.double(), 11, None, 1.0)
+    for n in range(2):
+        gates.assert_scalar(f'shrunk6/ssim[{n}]', d['ssim'][n].item(), o32['ssim'][n].item(), o64['ssim'][n].item())
+    x, y = (T(v) for v in cases.loss_case('rand_3x64x96')[::2])
+    d = ML.calc_ssim(x.cuda(), y.cuda(), window=ML.create_window(9).cuda(), data_range=1.0)
+    o32, o64 = OL.ssim(x, y, 9, None, 1.0), OL.ssim(x.double(), y.double(), 9, None, 1.0)
+    for n in range(3):
+        gates.assert_scalar(f'window9/ssim[{n}]', d['ssim'][n].item(), o32['ssim'][n].item(), o64['ssim'][n].item())
+    with pytest.raises(NotImplementedError):
+        ML.calc_ssim(x.cuda(), y.cuda(), window=torch.ones(1, 1, 5, 5) / 25.0, data_range=1.0)
+    with pytest.raises(RuntimeError):
+        ML.SSIM(11, 1.0).cuda()(a.cuda(), f.cuda())       # the module keeps its 11-tap window: conv2d fails in the reference too
+    g = torch.Generator().manual_seed(77)
+    p, q = (torch.rand(2, 1, 208, 240, generator=g) for _ in range(2))
+    q = (0.6 * p + 0.4 * q).contiguous()
+    ms = ML.calc_msssim(p.cuda(), q.cuda(), data_range=1.0)
+    o32, o64 = OL.msssim(p, q, 11, None, None, 1.0), OL.msssim(p.double(), q.double(), 11, None, None, 1.0)
+    for n in range(2):
+        gates.assert_scalar(f'calc_msssim[{n}]', ms[n].item(), o32[n].item(), o64[n].item())
+
+
+def test_ms_ssim_module_generic_window():
+    """MS_SSIM(win_size=13) (loss.py:188-208): the module's 13-tap window on every pyramid level through the generic kernels,
+    value and gradient w.r.t. the second image."""
+    ML = _mods()
+    g = torch.Generator().manual_seed(78)
+    a, f = (torch.rand(2, 1, 224, 240, generator=g) for _ in range(2))
+    f = (0.6 * a + 0.4 * f).contiguous()
+    w = torch.tensor([1.0, -0.5])
+    mod = ML.MS_SSIM(13, 1.0).cuda()
+    F_ = f.cuda().requires_grad_(True)
+    ms = mod(a.cuda(), F_)
+    o32 = OL.msssim(a, f, 13, None, None, 1.0)
+    f64 = f.double().requires_grad_(True)
+    o64 = OL.msssim(a.double(), f64, 13, None, None, 1.0)
+    for n in range(2):
+        gates.assert_scalar(f'ms-ssim win13[{n}]', ms[n].item(), o32[n].item(), o64[n].item())
+    (w.cuda() * ms).sum().backward()
+    (w.double() * o64).sum().backward()
+    f32 = f.clone().requires_grad_(True)
+    (w * OL.msssim(a, f32, 13, None, None, 1.0)).sum().backward()
+    frac, mx, where = gates.grad_report(F_.grad.cpu().numpy(), f64.grad.numpy())
+    ref_err = np.abs(f32.grad.numpy() - f64.grad.numpy()).max() / np.abs(f64.grad.numpy()).max()
+    assert mx <= max(1e-5, ref_err), f'max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
