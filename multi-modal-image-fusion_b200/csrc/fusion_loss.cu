@@ -96,24 +96,50 @@ static double simulate_makespan(int H, int cols, int T, int n_tall, int s, int e
     return makespan;
 }
 
-static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
+// The same for the warp-specialised kernel: ONE CTA per SM, so plain list scheduling on 148 machines.
+static double simulate_makespan_1(int H, int cols, int T, int n_tall, int s, int extra) {
+    constexpr int kSM = 148;
+    const int nseg = geom_nseg(H, T, n_tall, s);
+    const long long total = (long long)cols * nseg;
+    std::priority_queue<double, std::vector<double>, std::greater<double>> pq;
+    for (int k = 0; k < kSM; ++k) pq.push(0.0);
+    double makespan = 0.0;
+    for (long long idx = 0; idx < total; ++idx) {
+        const int seg = (int)(idx / cols);
+        int i0, i1;
+        if (seg < n_tall) { i0 = seg * T; i1 = i0 + T; } else { i0 = n_tall * T + (seg - n_tall) * s; i1 = i0 + s; }
+        if (i1 > H) i1 = H;
+        const double t = pq.top() + (double)(i1 - i0 + extra);
+        pq.pop();
+        pq.push(t);
+        if (t > makespan) makespan = t;
+    }
+    return makespan;
+}
+
+// ws: geometry for fusion_loss_ws_kernel (one CTA per SM) instead of fusion_loss_bwd_kernel (two)
+static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     BwdGeom g;
     g.Hout = H - (win - 1); g.Wout = W - (win - 1);
     g.nstrip = ceil_div(W, bwd_tg(win));
-    const int extra = 2 * (win - 1) + 8;                      // halo + batch rounding + prologue, in rows
-    g.seg_rows = pick_seg_rows(H, B * g.nstrip, 2 * 148, extra, 0.72);   // 2 CTAs / SM
+    // halo + batch rounding + prologue, in rows; the warp-specialised pipeline also fills and drains (3 stages)
+    const int extra = 2 * (win - 1) + 8 + (ws ? 16 : 0);
+    g.seg_rows = ws ? pick_seg_rows(H, B * g.nstrip, 148, extra, 0.0) : pick_seg_rows(H, B * g.nstrip, 2 * 148, extra, 0.72);
     g.seg_short = g.seg_rows; g.n_tall = ceil_div(H, g.seg_rows);
     g.nseg = g.n_tall;
     // memo: the search below simulates a few dozen schedules (~1 ms); a training loop asks for one shape
-    struct Key { int B, H, W, win; BwdGeom g; };
+    struct Key { int B, H, W, win; bool ws; BwdGeom g; };
     static thread_local Key memo[8];
     static thread_local int memo_n = 0, memo_next = 0;
     for (int i = 0; i < memo_n; ++i)
-        if (memo[i].B == B && memo[i].H == H && memo[i].W == W && memo[i].win == win) return memo[i].g;
+        if (memo[i].B == B && memo[i].H == H && memo[i].W == W && memo[i].win == win && memo[i].ws == ws) return memo[i].g;
     const int cols = B * g.nstrip;
     static const bool uniform_only = getenv("MMIF_UNIFORM_SEGMENTS") != nullptr;      // A/B switch for the measurements
+    auto simulate = [&](int T, int n_tall, int s) {
+        return ws ? simulate_makespan_1(H, cols, T, n_tall, s, extra) : simulate_makespan(H, cols, T, n_tall, s, extra);
+    };
     if (!uniform_only && (long long)cols * g.nseg <= 40000 && g.seg_rows >= 32) {
-        double best = simulate_makespan(H, cols, g.seg_rows, g.n_tall, g.seg_rows, extra);
+        double best = simulate(g.seg_rows, g.n_tall, g.seg_rows);
         const BwdGeom uni = g;
         const int talls[4] = {uni.seg_rows, (uni.seg_rows * 5 / 4 + 7) / 8 * 8, (uni.seg_rows * 3 / 2 + 7) / 8 * 8, uni.seg_rows * 2};
         const int divs[5] = {2, 3, 4, 6, 8};
@@ -126,7 +152,7 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
                 for (int nt = (full > 3 ? full - 3 : 0); nt * T < H; ++nt) {
                     const int nseg = geom_nseg(H, T, nt, sh);
                     if ((long long)cols * nseg > 40000) continue;
-                    const double m = simulate_makespan(H, cols, T, nt, sh, extra);
+                    const double m = simulate(T, nt, sh);
                     if (m < best * 0.985) { best = m; g.seg_rows = T; g.seg_short = sh; g.n_tall = nt; g.nseg = nseg; }
                 }
             }
@@ -134,10 +160,10 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11) {
     }
     static const bool debug_geom = getenv("MMIF_DEBUG_GEOM") != nullptr;
     if (debug_geom)
-        fprintf(stderr, "[mmif] bwd geometry B=%d H=%d W=%d win=%d: %d strips, %d segments = %d x %d rows + %d x %d rows\n", B, H, W, win,
+        fprintf(stderr, "[mmif] bwd geometry%s B=%d H=%d W=%d win=%d: %d strips, %d segments = %d x %d rows + %d x %d rows\n", ws ? " (ws)" : "", B, H, W, win,
                 g.nstrip, g.nseg, g.n_tall < g.nseg ? g.n_tall : g.nseg, g.seg_rows, g.nseg > g.n_tall ? g.nseg - g.n_tall : 0, g.seg_short);
     Key& k = memo[memo_next];
-    k.B = B; k.H = H; k.W = W; k.win = win; k.g = g;
+    k.B = B; k.H = H; k.W = W; k.win = win; k.ws = ws; k.g = g;
     memo_next = (memo_next + 1) % 8;
     if (memo_n < 8) ++memo_n;
     return g;
@@ -574,6 +600,10 @@ fusion_loss_bwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_co
     }
 }
 
+}  // namespace mmif
+#include "fusion_loss_ws.cuh"
+namespace mmif {
+
 // Companion of the early exit above: dF = g * dF_unit when the three upstream gradients are equal,
 // nothing otherwise (the recomputing kernel then does the work).  Pure streaming, 8 B/pixel.
 __global__ void __launch_bounds__(256)
@@ -638,6 +668,11 @@ static size_t loss_ws_core_bytes(int B, int H, int W) {
         const size_t z = ws_counters_bytes(B) + (size_t)B * g.nstrip * g.nseg * 8 * sizeof(double);
         best = best > f ? best : f;
         best = best > z ? best : z;
+        if (wins[k] == WIN11) {
+            const BwdGeom gw = bwd_geom(B, H, W, WIN11, true);
+            const size_t zw = ws_counters_bytes(B) + (size_t)B * gw.nstrip * gw.nseg * 8 * sizeof(double);
+            best = best > zw ? best : zw;
+        }
     }
     return best;
 }
@@ -654,7 +689,11 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
                       const Upstream& up, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
                       cudaStream_t st, const BwdExtra* ex = nullptr) {
     const int win = (ex && ex->win) ? ex->win : WIN11;
-    const BwdGeom g = bwd_geom(B, H, W, win);
+    // the training objective runs on the warp-specialised kernel; MMIF_LOSS_WS=0 is the A/B switch back to the 2-CTA kernel
+    const char* ws_env = getenv("MMIF_LOSS_WS");            // read per call: the A/B tools flip it inside one process
+    const bool ws_off = ws_env != nullptr && atoi(ws_env) == 0;
+    const bool use_ws = !ex && win == WIN11 && !ws_off;
+    const BwdGeom g = bwd_geom(B, H, W, win, use_ws);
     BwdParams p;
     memset(&p, 0, sizeof(p));
     p.x1 = i1; p.x2 = i2; p.y = f; p.dF = dF; p.dF_unit = dF_unit;
@@ -702,6 +741,11 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<7, false, false, true>, at, sz));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false, true>, at, sz));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false, true>, at, sz));
+        const int szw = (int)sizeof(SmemWS);
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, false>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, false>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, true>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, true>, at, szw));
     }
     dim3 grid(g.nstrip, B, g.nseg);
     if (!zmode && dF_unit) {
@@ -726,6 +770,15 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
             case 5: fusion_loss_bwd_kernel<5, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
             case 3: fusion_loss_bwd_kernel<3, false, false, true><<<grid, kNT, sm, st>>>(m1, m2, my, p); break;
             default: set_error("no backward kernel for window %d", win); return MMIF_E_MODE;
+        }
+    } else if (use_ws) {
+        const size_t smw = sizeof(SmemWS);
+        if (zmode) {
+            if (fast) fusion_loss_ws_kernel<11, true, true><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
+            else fusion_loss_ws_kernel<11, false, true><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
+        } else {
+            if (fast) fusion_loss_ws_kernel<11, true, false><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
+            else fusion_loss_ws_kernel<11, false, false><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
         }
     } else if (zmode) {
         if (fast) fusion_loss_bwd_kernel<11, true, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);

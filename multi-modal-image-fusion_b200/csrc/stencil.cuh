@@ -198,10 +198,10 @@ __device__ __forceinline__ void vpass_moments(SM& sm, const Taps& tp, const Shif
 // ---- H-pass: horizontal WIN-tap blur, 8 pixels x NM packed maps per thread -------------------
 // src row pointer = buffer + o*pitch + 8*g (float2 units); map stride `mstride`.
 // REV: use taps reversed (adjoint pass).  Results in acc[j][m].
-template <int WIN, int NM, bool REV>
-__device__ __forceinline__ void hpass(const float2* __restrict__ src, int mstride, const Taps& tp, float2 (&acc)[8][NM]) {
+template <int WIN, int NM, bool REV, int NOUT = 8>
+__device__ __forceinline__ void hpass(const float2* __restrict__ src, int mstride, const Taps& tp, float2 (&acc)[NOUT][NM]) {
 #pragma unroll
-    for (int kk = 0; kk < 8 + WIN - 1; kk += 2) {
+    for (int kk = 0; kk < NOUT + WIN - 1; kk += 2) {
         float4 q[NM];
 #pragma unroll
         for (int m = 0; m < NM; ++m) q[m] = *reinterpret_cast<const float4*>(src + m * mstride + kk);
@@ -209,7 +209,7 @@ __device__ __forceinline__ void hpass(const float2* __restrict__ src, int mstrid
         for (int half = 0; half < 2; ++half) {
             const int col = kk + half;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NOUT; ++j) {
                 const int k = col - j;
                 if (k >= 0 && k < WIN) {
                     const float w = REV ? tp.w[WIN - 1 - k] : tp.w[k];
