@@ -96,24 +96,42 @@ static double simulate_makespan(int H, int cols, int T, int n_tall, int s, int e
     return makespan;
 }
 
-// The same for the warp-specialised kernel: ONE CTA per SM, so plain list scheduling on 148 machines.
+// The same for the warp-specialised kernel: ONE CTA per SM, so plain list scheduling on 148 machines.  The CTAs come in at most
+// three classes of equal length dispatched in order (tall segments, short segments, the ragged last segment), so the machines
+// are tracked as a handful of (load, count) groups: exact, and ~total / 148 steps instead of total heap operations.
 static double simulate_makespan_1(int H, int cols, int T, int n_tall, int s, int extra) {
     constexpr int kSM = 148;
     const int nseg = geom_nseg(H, T, n_tall, s);
-    const long long total = (long long)cols * nseg;
-    std::priority_queue<double, std::vector<double>, std::greater<double>> pq;
-    for (int k = 0; k < kSM; ++k) pq.push(0.0);
-    double makespan = 0.0;
-    for (long long idx = 0; idx < total; ++idx) {
-        const int seg = (int)(idx / cols);
+    struct Grp { double load; int cnt; };
+    Grp grp[16];
+    int ng = 1;
+    grp[0] = Grp{0.0, kSM};
+    for (int seg = 0; seg < nseg; ++seg) {
         int i0, i1;
         if (seg < n_tall) { i0 = seg * T; i1 = i0 + T; } else { i0 = n_tall * T + (seg - n_tall) * s; i1 = i0 + s; }
         if (i1 > H) i1 = H;
-        const double t = pq.top() + (double)(i1 - i0 + extra);
-        pq.pop();
-        pq.push(t);
-        if (t > makespan) makespan = t;
+        const double len = (double)(i1 - i0 + extra);
+        int n = cols;
+        while (n > 0) {
+            int lo = 0;
+            for (int k = 1; k < ng; ++k)
+                if (grp[k].load < grp[lo].load) lo = k;
+            const int take = grp[lo].cnt < n ? grp[lo].cnt : n;
+            const double nl = grp[lo].load + len;
+            grp[lo].cnt -= take;
+            if (grp[lo].cnt == 0) grp[lo] = grp[--ng];
+            int hit = -1;
+            for (int k = 0; k < ng; ++k)
+                if (grp[k].load == nl) hit = k;
+            if (hit >= 0) grp[hit].cnt += take;
+            else if (ng < 16) grp[ng++] = Grp{nl, take};
+            else { grp[0].cnt += take; if (grp[0].load < nl) grp[0].load = nl; }      // cannot happen with three classes
+            n -= take;
+        }
     }
+    double makespan = 0.0;
+    for (int k = 0; k < ng; ++k)
+        if (grp[k].cnt > 0 && grp[k].load > makespan) makespan = grp[k].load;
     return makespan;
 }
 
@@ -123,7 +141,8 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     g.Hout = H - (win - 1); g.Wout = W - (win - 1);
     g.nstrip = ceil_div(W, bwd_tg(win));
     // halo + batch rounding + prologue, in rows; the warp-specialised pipeline also fills and drains (3 stages)
-    const int extra = 2 * (win - 1) + 8 + (ws ? 16 : 0);
+    static const int ws_extra = getenv("MMIF_WS_EXTRA") ? atoi(getenv("MMIF_WS_EXTRA")) : 12;
+    const int extra = 2 * (win - 1) + 8 + (ws ? ws_extra : 0);
     g.seg_rows = ws ? pick_seg_rows(H, B * g.nstrip, 148, extra, 0.0) : pick_seg_rows(H, B * g.nstrip, 2 * 148, extra, 0.72);
     g.seg_short = g.seg_rows; g.n_tall = ceil_div(H, g.seg_rows);
     g.nseg = g.n_tall;
@@ -138,7 +157,29 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     auto simulate = [&](int T, int n_tall, int s) {
         return ws ? simulate_makespan_1(H, cols, T, n_tall, s, extra) : simulate_makespan(H, cols, T, n_tall, s, extra);
     };
-    if (!uniform_only && (long long)cols * g.nseg <= 40000 && g.seg_rows >= 32) {
+    if (ws && !uniform_only) {
+        // one CTA per SM: the closed-form tail term of pick_seg_rows ranks the candidates wrongly (B = 64: one 3072-row segment,
+        // 17 waves, instead of two of 1536, 33 waves; measured 15.03 vs 14.86 ms), while list scheduling simulated on 148 SMs
+        // with 40 rows of per-CTA overhead reproduces every measured ordering (tools/ws_geom_scan.sh).  Full search: tall
+        // heights H / k (k = 1..24), short heights T / {1, 2, 3, 4, 6, 8}, every count of tall segments.
+        double best = 1e300;
+        const int divs[6] = {1, 2, 3, 4, 6, 8};
+        for (int k = 1; k <= 24; ++k) {
+            const int T = ceil_div(ceil_div(H, k), 8) * 8;
+            if (T < 32 && k > 1) break;
+            for (int di = 0; di < 6; ++di) {
+                const int sh = ceil_div(ceil_div(T, divs[di]), 8) * 8;
+                if (sh < 16 || (di > 0 && sh >= T)) continue;
+                const int full = ceil_div(H, T);
+                for (int nt = (di == 0 ? full : 0); nt <= full && (nt == full || nt * T < H); ++nt) {
+                    const int nseg = geom_nseg(H, T, nt, sh);
+                    if ((long long)cols * nseg > 40000) continue;
+                    const double m = simulate_makespan_1(H, cols, T, nt, sh, extra);
+                    if (m < best * (di == 0 ? 1.0 : 0.995)) { best = m; g.seg_rows = T; g.seg_short = sh; g.n_tall = nt < nseg ? nt : nseg; g.nseg = nseg; }
+                }
+            }
+        }
+    } else if (!uniform_only && (long long)cols * g.nseg <= 40000 && g.seg_rows >= 32) {
         double best = simulate(g.seg_rows, g.n_tall, g.seg_rows);
         const BwdGeom uni = g;
         const int talls[4] = {uni.seg_rows, (uni.seg_rows * 5 / 4 + 7) / 8 * 8, (uni.seg_rows * 3 / 2 + 7) / 8 * 8, uni.seg_rows * 2};
@@ -692,7 +733,11 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     // the training objective runs on the warp-specialised kernel; MMIF_LOSS_WS=0 is the A/B switch back to the 2-CTA kernel
     const char* ws_env = getenv("MMIF_LOSS_WS");            // read per call: the A/B tools flip it inside one process
     const bool ws_off = ws_env != nullptr && atoi(ws_env) == 0;
-    const bool use_ws = !ex && win == WIN11 && !ws_off;
+    const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
+                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
+    // (the other combine / norm modes run the general Sobel path on every batch: one long dependency chain per row, which a
+    // single warp group cannot hide — measured 3.45 vs 2.85 ms at 8x3072x4096 — so they stay on the 2-CTA kernel)
+    const bool use_ws = !ex && win == WIN11 && fast && !ws_off;
     const BwdGeom g = bwd_geom(B, H, W, win, use_ws);
     BwdParams p;
     memset(&p, 0, sizeof(p));
@@ -743,9 +788,7 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false, true>, at, sz));
         const int szw = (int)sizeof(SmemWS);
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, false>, at, szw));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, false>, at, szw));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, true>, at, szw));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, true>, at, szw));
     }
     dim3 grid(g.nstrip, B, g.nseg);
     if (!zmode && dF_unit) {
@@ -758,8 +801,6 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         // already knows the upstream gradients are equal and the recomputing kernel (which would exit at once) is not launched
         if (up.g[0] && up.g[0] == up.g[1] && up.g[1] == up.g[2]) return MMIF_OK;
     }
-    const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
-                      cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
     const size_t sm = sizeof(SmemBwd);
     if (ex) {                         // SSIM-only extended launches ('w-ssim', MS-SSIM levels, MSW-SSIM windows)
         if (zmode || p.do_sobel) { set_error("extended backward is SSIM-only"); return MMIF_E_MODE; }
@@ -773,13 +814,8 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         }
     } else if (use_ws) {
         const size_t smw = sizeof(SmemWS);
-        if (zmode) {
-            if (fast) fusion_loss_ws_kernel<11, true, true><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
-            else fusion_loss_ws_kernel<11, false, true><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
-        } else {
-            if (fast) fusion_loss_ws_kernel<11, true, false><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
-            else fusion_loss_ws_kernel<11, false, false><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
-        }
+        if (zmode) fusion_loss_ws_kernel<11, true, true><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
+        else fusion_loss_ws_kernel<11, true, false><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
     } else if (zmode) {
         if (fast) fusion_loss_bwd_kernel<11, true, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
         else fusion_loss_bwd_kernel<11, false, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);

@@ -25,6 +25,9 @@ constexpr int kWsNT = 512;
 #define MMIF_WS_SLEEP_NS 40
 #endif
 constexpr unsigned kWsSleepNs = MMIF_WS_SLEEP_NS;
+#ifndef MMIF_WS_V_ROLLED
+#define MMIF_WS_V_ROLLED 0
+#endif
 constexpr int kWsGroupBytes = 3 * kRB * kRPB * 4;
 
 struct SmemWS {
@@ -208,6 +211,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                 const float* q0 = &sm.ring[0][slot * kRB][t + kVOFF];
                 const float* q2 = &sm.ring[0][s1 * kRB][t + kVOFF];
                 const float* q4 = &sm.ring[0][s2 * kRB][t + kVOFF];
+#if MMIF_WS_V_ROLLED
                 const float* q1 = q0 + 4 * kRPB;
                 const float* q3 = q2 + 4 * kRPB;
 #pragma unroll 1
@@ -239,6 +243,35 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                     }
                     vb += 4 * kVPitch;
                 }
+#else
+                {   // one pass of eight output rows over the 18 input rows (three ring slots, constant offsets inside a slot)
+                    const float* sg[3] = {q0, q2, q4};
+                    float2 acc[kRB][4];
+#pragma unroll
+                    for (int rr = 0; rr < kRB + WIN - 1; ++rr) {
+                        const float* rp = sg[rr >> 3] + (rr & 7) * kRPB;
+                        const float y = rp[2 * kWsRows * kRPB] - sh.cy;
+                        float2 P[4];
+                        P[0] = add2(f2(rp[0], rp[kWsRows * kRPB]), negc);
+                        P[1] = mul2(P[0], P[0]);
+                        P[2] = muls(y, P[0]);
+                        P[3] = f2(y, y * y);
+#pragma unroll
+                        for (int o = 0; o < kRB; ++o) {
+                            const int k = rr - o;
+                            if (k >= 0 && k < WIN) {
+#pragma unroll
+                                for (int m = 0; m < 4; ++m) acc[o][m] = (k == 0) ? muls(p.taps.w[0], P[m]) : fmas(p.taps.w[k], P[m], acc[o][m]);
+                            }
+                        }
+                        if (rr >= WIN - 1) {
+                            const int o = rr - (WIN - 1);
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) vb[o * kVPitch + m * kVCols + t] = acc[o][m];
+                        }
+                    }
+                }
+#endif
             }
             nb_arrive(NB_VFULL + (b & 1));
             slot = (slot + 1 == kWsSlots) ? 0 : slot + 1;

@@ -281,8 +281,11 @@ def test_kernel_names_seen_by_cupti():
         pytest.skip(f'profiler unavailable: {exc}')
     if not names:
         pytest.skip('CUPTI recorded no kernels')
-    assert any('fusion_loss_bwd_kernel<11, true, true, false>' in n.replace('(bool)1', 'true').replace('(bool)0', 'false')
-               or ('fusion_loss_bwd_kernel' in n and '1, 1, 0' in n.replace('(bool)', '')) for n in names), names
+    # the single-pass instantiation: the warp-specialised kernel <11, FAST, ZMODE> (or, with MMIF_LOSS_WS=0, the 2-CTA kernel)
+    norm = [n.replace('(bool)1', 'true').replace('(bool)0', 'false').replace('(bool)', '') for n in names]
+    assert any('fusion_loss_ws_kernel<11, true, true>' in n or ('fusion_loss_ws_kernel' in n and '1, 1>' in n)
+               or 'fusion_loss_bwd_kernel<11, true, true, false>' in n or ('fusion_loss_bwd_kernel' in n and '1, 1, 0' in n)
+               for n in norm), names
     assert any('rescale_unit_kernel' in n for n in names), names
     assert not any('moment_fwd_kernel' in n for n in names), names
 
