@@ -207,7 +207,7 @@ def main():
         y = f.detach().requires_grad_(True)              # a fresh imgf every step, as the network produces one
         if ev:
             ev[0].record()
-        l1 = fn1(a, b, y)                                # launches fusion_loss_bwd_kernel<11,1,1,0>: loss values + d(total)/d imgf
+        l1 = fn1(a, b, y)                                # launches fusion_loss_ws_kernel<11,1,1>: loss values + d(total)/d imgf
         if ev:
             ev[1].record()
         total = l1 + fn2(a, b, y, mode='max') + fn3(a, b, y, mode='max')      # the other two read the same launch
@@ -299,12 +299,12 @@ def main():
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             tj = json.load(fh)
-        ent = tj['fusion_loss_bwd_kernel<FAST,ZMODE>']
+        ent = tj.get('fusion_loss_ws_kernel<FAST,ZMODE>') or tj['fusion_loss_bwd_kernel<FAST,ZMODE>']
         traffic = ent['dram_bytes_per_pixel'] * local_pix
         traffic_src = 'stored constant: ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel (%s), per pixel x the pixels of one launch; not measured in this run' % ent.get('capture', 'profiles/traffic.json')
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_bwd_kernel<11, FAST=1, ZMODE=1, EXT=0> (loss values + dIf, one launch) as launched by core.loss.SSIMLoss',
+    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_ws_kernel<11, FAST=1, ZMODE=1> (warp-specialised: loss values + dIf, one launch) as launched by core.loss.SSIMLoss',
                 'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
                 'ms_per_launch': ms_z,
@@ -320,7 +320,7 @@ def main():
     two_kernel = {'value': total_mpix / (ms_step2 * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step2,
                   'fwd': {'kernel': 'moment_fwd_kernel<11,EPI_SSIM>', 'ms_per_launch': ms_fwd, 'achieved': gbs(ALG_BYTES_FWD, ms_fwd),
                           'frac': gbs(ALG_BYTES_FWD, ms_fwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_FWD},
-                  'bwd': {'kernel': 'fusion_loss_bwd_kernel<FAST=1,ZMODE=0>', 'ms_per_launch': ms_bwd, 'achieved': gbs(ALG_BYTES_BWD, ms_bwd),
+                  'bwd': {'kernel': 'fusion_loss_ws_kernel<FAST=1,ZMODE=0>', 'ms_per_launch': ms_bwd, 'achieved': gbs(ALG_BYTES_BWD, ms_bwd),
                           'frac': gbs(ALG_BYTES_BWD, ms_bwd) / peak, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD},
                   'combined_28B': {'achieved': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd),
                                    'frac': gbs(ALG_BYTES_FWD + ALG_BYTES_BWD, ms_fwd + ms_bwd) / peak},

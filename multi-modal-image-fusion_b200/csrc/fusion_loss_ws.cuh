@@ -1,19 +1,28 @@
 // Warp-specialised form of the loss + gradient kernel (included by fusion_loss.cu; same arithmetic, same tile geometry,
-// bit-identical gradients).
+// bit-identical gradients for equal row segments).
 //
 // Why: fusion_loss_bwd_kernel keeps all five phases of a batch in every thread, needs 255 registers for that and so runs
 // 2 CTAs x 4 warps per SM = TWO warps per scheduler; ncu (profiles/r2_zkernel.txt) shows the FP32 pipe 65 % busy with
 // the schedulers idle on `wait` / `short_scoreboard` / `no_instruction` / `barrier`: too few warps to cover each other.
-// Here ONE CTA of 384 threads owns the SM and its three warp groups are pipeline stages working on different batches
-// at the same time, handing the tile on through shared memory with mbarrier full / empty pairs (no CTA-wide barrier in
-// the batch loop):
-//   G0 (warps 0-3)  : TMA producer + Sobel / pixel adjoint S(b) -> gbuf[b % 4], vertical moments V(b) -> vbuf[b & 1]
-//   G1 (warps 4-7)  : horizontal moments + SSIM derivative coefficients H(b): vbuf[b & 1] -> cbuf[b & 1]
-//   G2 (warps 8-11) : vertical adjoint B1(b) (stateful) -> tbuf, horizontal adjoint + combine + store B2(b)
-// Each group keeps only its own phase's registers (<= 168), every scheduler holds three warps of three different phases
+// Here ONE CTA of 512 threads owns the SM and its four warp groups are pipeline stages working on different batches
+// at the same time, handing the tile on through shared memory (no CTA-wide barrier in the batch loop):
+//   G0 (warps 0-3)   : TMA producer + vertical moments V(b): ring -> vbuf[b & 1]
+//   G1 (warps 4-7)   : horizontal moments + SSIM derivative coefficients H(b): vbuf[b & 1] -> cbuf[b & 1]
+//   G2 (warps 8-11)  : Sobel / pixel adjoint S(b): ring -> gbuf[b & 1]
+//   G3 (warps 12-15) : vertical adjoint B1(b) (stateful) cbuf -> tbuf, horizontal adjoint + combine + store B2(b)
+// Each group keeps only its own phase's registers (<= 128), every scheduler holds four warps of four different phases
 // (FMA-heavy blur next to the issue-bound Sobel / epilogue code), and a stage never waits for the whole CTA.
-// Shared memory (208 KB of the SM's 227): 6-slot input ring (G2's combine reads rows three batches behind G0's prefetch),
-// double-buffered vbuf / cbuf, tbuf, 4 gbuf slots.
+// What the captures taught (profiles/r2b_ws_steps.txt), in the order it was learnt:
+//   * three or four instruction streams per SM thrash the 32 KB L1.5 instruction cache if the fully unrolled bodies
+//     (43 KB) are kept: `no_instruction` went from 0.27 to 2.33 stalls per issue.  H, S are therefore two passes over half
+//     the tile through ONE copy of the code (B1 / B2 / V stay unrolled: the total is ~30 KB) -> 0.2;
+//   * mbarrier try_wait / nanosleep polling by the waiting groups executed 40 % of all instructions; the SM's dispatch
+//     port turned out to be the binding resource (a packed FFMA2 holds it for two cycles: issue 62 % + packed shadows 30 %
+//     = 92-94 % busy), so the hand-overs between groups are HARDWARE named barriers (bar.arrive / bar.sync: a blocked warp
+//     issues nothing) and only the TMA ring keeps mbarriers;
+//   * with the port saturated the only remaining lever is the instruction count per batch (2.86 k per 8 x 128 tile now).
+// Shared memory (218 KB of the SM's 227): 7-slot input ring (G3's combine reads rows three batches behind G0's prefetch),
+// double-buffered vbuf / cbuf / gbuf, one tbuf.
 #pragma once
 
 namespace mmif {
@@ -52,6 +61,11 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // Wait with a suspend-time hint (the waiting warp sleeps in hardware until the phase completes: a spinning try_wait loop
 // was measured to execute HALF of the kernel's instructions and to starve the working warps of issue slots and
 // instruction fetches) and a watchdog: a protocol error traps (the launch fails) instead of hanging the GPU.
+// Every thread arrives (the plain-load ring: each thread publishes its own stores; also what compute-sanitizer's racecheck
+// can follow).
+__device__ __forceinline__ void mbar_arrive_each(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_wd(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok = 0;
@@ -146,7 +160,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kWsSlots; ++s) {
-            mbar_init((uint64_t*)&sm.ring_full[s], use_tma ? 1 : 4);
+            mbar_init((uint64_t*)&sm.ring_full[s], use_tma ? 1 : 128);
             mbar_init((uint64_t*)&sm.ring_empty[s], 8);         // warps of G2 (after S) + G3 (after B2)
         }
         mbar_fence_init();
@@ -185,7 +199,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                         }
                     }
                 }
-                mbar_arrive(&sm.ring_full[slot]);
+                mbar_arrive_each(&sm.ring_full[slot]);
             }
         };
         issue(0);
