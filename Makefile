@@ -8,7 +8,14 @@ LIB := $(PKG)/libmmif_b200.so
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2 \
            -Xptxas -v --expt-relaxed-constexpr
 
-all: $(LIB)
+PYINC := $(shell python3 -c "import sysconfig; print(sysconfig.get_paths()['include'])")
+FAST := $(PKG)/_fastcall.so
+
+all: $(LIB) $(FAST)
+
+# CPython fast-call binding of the per-step entries (optional: _lib.py falls back to ctypes without it)
+$(FAST): $(PKG)/csrc/fastcall.c include/mmif_b200.h $(LIB)
+	gcc -O2 -fPIC -shared -I$(PYINC) $< -o $@ -L$(PKG) -lmmif_b200 -Wl,-rpath,'$$ORIGIN'
 
 build/%.o: $(PKG)/csrc/%.cu $(HDR)
 	@mkdir -p build
@@ -19,5 +26,5 @@ $(LIB): $(OBJ)
 	$(NVCC) -shared -o $@ $(OBJ) -cudart static
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(FAST)
 .PHONY: all clean

@@ -118,9 +118,34 @@ def stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_int(device):
-    """cudaStream_t of torch's current stream on `device`, as a plain int."""
+    """cudaStream_t of torch's current stream on `device`, as a plain int (the raw getter: 0.2 us against the 11 us of
+    building a torch.cuda.Stream object, twice per training step)."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_fast = False
+
+
+def fastcall():
+    """The CPython fast-call binding of the per-step entries (csrc/fastcall.c -> _fastcall.so), or None if it was not built
+    (MMIF_NO_FASTCALL=1 forces the ctypes binding).  Same library, same entry points, ~0.5 us instead of ~9 us per call."""
+    global _fast
+    if _fast is False:
+        mod = None
+        if not os.environ.get('MMIF_NO_FASTCALL'):
+            load()
+            try:
+                from . import _fastcall as mod
+            except Exception:       # not built: ctypes serves the same entries
+                mod = None
+        _fast = mod
+    return _fast
 
 
 def call(device, fn, *args):

@@ -185,3 +185,26 @@ def test_gloo_world2_loss_reduction_and_sharded_eval():
             assert cols == single
         else:
             assert cols is None
+
+
+def test_fastcall_binding_loads_and_validates_without_gpu():
+    """The CPython fast-call binding (csrc/fastcall.c) resolves the same library entries as the ctypes binding: the same
+    return codes for the same invalid arguments, no compute call."""
+    import mmif_b200  # noqa: F401
+    from mmif_b200 import _lib as L
+    fc = L.fastcall()
+    assert fc is not None, '_fastcall.so was not built (make)'
+    lib = L.load()
+    cfg = L.MmifLossCfg()
+    cfg.pixel_combine = cfg.grad_combine = L.COMBINE['max']
+    cfg.pixel_norm = cfg.grad_norm = L.NORM['l1']
+    import ctypes
+    addr = ctypes.addressof(cfg)
+    rc_fast = fc.loss_fwd(None, None, None, 1, 32, 32, addr, None, None, None, 0, None)
+    rc_ct = lib.mmif_fusion_loss_fwd(None, None, None, 1, 32, 32, ctypes.byref(cfg), None, None, None, 0, None)
+    assert rc_fast == rc_ct != 0
+    rc_fast = fc.loss_bwd3(16, 16, 16, 1, 4, 4, addr, None, None, None, None, None, None, 0, None)      # shape too small
+    rc_ct = lib.mmif_fusion_loss_bwd3(16, 16, 16, 1, 4, 4, ctypes.byref(cfg), None, None, None, None, None, None, 0, None)
+    assert rc_fast == rc_ct != 0
+    with pytest.raises(TypeError):
+        fc.loss_fwd(1, 2, 3)

@@ -342,3 +342,42 @@ def test_calling_the_losses_twice_on_the_same_tensors_builds_two_graphs():
     sum(_three(ML, a, b, F_)).backward()            # same tensor objects, same versions
     assert L.launch_counts()['loss_single_pass'] - c0['loss_single_pass'] == 1
     assert torch.equal(F_.grad, g1)
+
+
+def test_fastcall_binding_equals_the_ctypes_binding():
+    """The per-step entries through the CPython fast-call binding and through ctypes: the same kernels, bit-equal outputs."""
+    L, ML = _mods()
+    fc = L.fastcall()
+    assert fc is not None
+    lib = L.load()
+    a, b, f = (T(x).cuda() for x in cases.loss_case('rand_3x64x96'))
+    B, H, W = a.shape[0], a.shape[2], a.shape[3]
+    cfg = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
+    cfg.want_grad = 1
+    st = L.stream_int(a.device)
+    res = []
+    for fast in (False, True):
+        out = torch.zeros(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device='cuda')
+        ws = torch.zeros(lib.mmif_loss_workspace_bytes(B, H, W), dtype=torch.uint8, device='cuda')
+        dU = torch.zeros_like(f)
+        if fast:
+            rc = fc.loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.addressof(cfg), out.data_ptr(), dU.data_ptr(),
+                             ws.data_ptr(), ws.numel(), st)
+        else:
+            rc = lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(),
+                                          dU.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        assert rc == 0
+        g = torch.tensor([2.0, 0.5, 3.0], device='cuda')
+        dF = torch.zeros_like(f)
+        cfg0 = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
+        if fast:
+            rc = fc.loss_bwd3(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.addressof(cfg0), g[0:1].data_ptr(),
+                              g[1:2].data_ptr(), g[2:3].data_ptr(), None, dF.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        else:
+            rc = lib.mmif_fusion_loss_bwd3(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg0), g[0:1].data_ptr(),
+                                           g[1:2].data_ptr(), g[2:3].data_ptr(), None, dF.data_ptr(), ws.data_ptr(), ws.numel(), st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        res.append((out.clone(), dU.clone(), dF.clone()))
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
