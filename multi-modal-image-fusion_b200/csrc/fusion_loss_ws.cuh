@@ -342,11 +342,13 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                         ab[j] = vj ? f2(a.x + a.y, nbv.x + nbv.y) : f2(0.f, 0.f);
                         cc[j] = vj ? ch : f2(0.f, 0.f);
                         if (ZMODE) {
-                            const bool zq = (zmh >> j) & 1u;
-                            const float2 sg = max2(vk, 1e-4f);
-                            z_ss = add2(z_ss, f2(zq ? S.x : 0.f, zq ? S.y : 0.f));
-                            z_cs = add2(z_cs, f2(zq ? Cs.x : 0.f, zq ? Cs.y : 0.f));
-                            z_sg = add2(z_sg, f2(zq ? sg.x : 0.f, zq ? sg.y : 0.f));
+                            // predicated adds (never a multiply by 0: the window columns past the strip are computed on
+                            // never-written pad columns of vbuf whose stale bits can be NaN / Inf)
+                            if ((zmh >> j) & 1u) {
+                                z_ss = add2(z_ss, S);
+                                z_cs = add2(z_cs, Cs);
+                                z_sg = add2(z_sg, max2(vk, 1e-4f));
+                            }
                         }
                     }
                 } else {
