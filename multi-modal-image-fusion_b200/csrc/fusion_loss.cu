@@ -150,7 +150,15 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     struct Key { int B, H, W, win; bool ws; BwdGeom g; };
     static thread_local Key memo[8];
     static thread_local int memo_n = 0, memo_next = 0;
-    for (int i = 0; i < memo_n; ++i)
+    const bool forced = ws && getenv("MMIF_WS_GEOM") != nullptr;
+    if (forced) {                // measurement aid: MMIF_WS_GEOM="T,n_tall,s" forces the segments (tools/ws_geom_force.py)
+        int fT = 0, fn = 0, fs = 0;
+        if (sscanf(getenv("MMIF_WS_GEOM"), "%d,%d,%d", &fT, &fn, &fs) == 3 && fT >= 16 && fs >= 16 && fT % 8 == 0 && fs % 8 == 0) {
+            g.seg_rows = fT; g.seg_short = fs; g.nseg = geom_nseg(H, fT, fn, fs); g.n_tall = fn < g.nseg ? fn : g.nseg;
+            return g;
+        }
+    }
+    for (int i = 0; i < memo_n && !forced; ++i)
         if (memo[i].B == B && memo[i].H == H && memo[i].W == W && memo[i].win == win && memo[i].ws == ws) return memo[i].g;
     const int cols = B * g.nstrip;
     static const bool uniform_only = getenv("MMIF_UNIFORM_SEGMENTS") != nullptr;      // A/B switch for the measurements
