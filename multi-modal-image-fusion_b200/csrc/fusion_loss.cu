@@ -8,6 +8,7 @@
 //                     adjoint blur and the folded Sobel adjoint and writes dL/dIf once
 //                     (12 B read + 4 B written per pixel).  One launch.
 #include <stdlib.h>
+#include <mutex>
 #include <queue>
 #include <vector>
 #include "moment_fwd.cuh"
@@ -148,8 +149,13 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     g.nseg = g.n_tall;
     // memo: the search below simulates a few dozen schedules (~1 ms); a training loop asks for one shape
     struct Key { int B, H, W, win; bool ws; BwdGeom g; };
-    static thread_local Key memo[8];
-    static thread_local int memo_n = 0, memo_next = 0;
+    // process-wide (the backward runs on autograd's thread and must not repeat the search) and large enough for a training
+    // loop that alternates a few shapes: one shape occupies six entries (five windows + the warp-specialised geometry)
+    constexpr int kMemo = 96;
+    static Key memo[kMemo];
+    static int memo_n = 0, memo_next = 0;
+    static std::mutex memo_mu;
+    std::unique_lock<std::mutex> memo_lock(memo_mu);
     const bool forced = ws && getenv("MMIF_WS_GEOM") != nullptr;
     if (forced) {                // measurement aid: MMIF_WS_GEOM="T,n_tall,s" forces the segments (tools/ws_geom_force.py)
         int fT = 0, fn = 0, fs = 0;
@@ -160,6 +166,7 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     }
     for (int i = 0; i < memo_n && !forced; ++i)
         if (memo[i].B == B && memo[i].H == H && memo[i].W == W && memo[i].win == win && memo[i].ws == ws) return memo[i].g;
+    memo_lock.unlock();          // the search below takes milliseconds: run it unlocked (a duplicate entry is harmless)
     const int cols = B * g.nstrip;
     static const bool uniform_only = getenv("MMIF_UNIFORM_SEGMENTS") != nullptr;      // A/B switch for the measurements
     auto simulate = [&](int T, int n_tall, int s) {
@@ -211,10 +218,11 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     if (debug_geom)
         fprintf(stderr, "[mmif] bwd geometry%s B=%d H=%d W=%d win=%d: %d strips, %d segments = %d x %d rows + %d x %d rows\n", ws ? " (ws)" : "", B, H, W, win,
                 g.nstrip, g.nseg, g.n_tall < g.nseg ? g.n_tall : g.nseg, g.seg_rows, g.nseg > g.n_tall ? g.nseg - g.n_tall : 0, g.seg_short);
+    memo_lock.lock();
     Key& k = memo[memo_next];
     k.B = B; k.H = H; k.W = W; k.win = win; k.ws = ws; k.g = g;
-    memo_next = (memo_next + 1) % 8;
-    if (memo_n < 8) ++memo_n;
+    memo_next = (memo_next + 1) % kMemo;
+    if (memo_n < kMemo) ++memo_n;
     return g;
 }
 
