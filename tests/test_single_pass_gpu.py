@@ -381,3 +381,44 @@ def test_fastcall_binding_equals_the_ctypes_binding():
         res.append((out.clone(), dU.clone(), dF.clone()))
     for x, y in zip(*res):
         assert torch.equal(x, y)
+
+
+def test_warp_specialised_kernel_equals_the_two_cta_kernel_on_a_shape_sweep(monkeypatch):
+    """The training configuration runs on fusion_loss_ws_kernel (one CTA per SM, four warp groups over named barriers);
+    MMIF_LOSS_WS=0 puts it back on the 2-CTA kernel.  Same arithmetic: on 40 shapes from 11 x 11 up (single batch / single
+    strip, ragged last batches, widths TMA cannot describe, several strips and segments) the loss blocks agree to 1e-6 and
+    the gradients to 2e-6 of max|g| (they are bit-equal when both kernels cut the rows alike; different row segments move
+    the tile shift constants), for the single-pass launch and for the recomputing backward with unequal upstreams."""
+    L, ML = _mods()
+    lib = L.load()
+    rng = np.random.RandomState(11)
+    shapes = [(1, 11, 11), (2, 11, 40), (1, 40, 11), (1, 12, 128), (3, 19, 109), (1, 27, 217), (2, 64, 96), (1, 300, 2050)]
+    shapes += [(int(rng.randint(1, 4)), int(rng.randint(11, 90)), int(rng.randint(11, 330))) for _ in range(32)]
+    for (B, H, W) in shapes:
+        g = torch.Generator().manual_seed(B * 1000003 + H * 1009 + W)
+        a, b, f = (torch.rand(B, 1, H, W, generator=g).cuda() for _ in range(3))
+        st = L.stream_int(a.device)
+        res = {}
+        for ws_on in ('0', '1'):
+            monkeypatch.setenv('MMIF_LOSS_WS', ws_on)
+            cfg = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
+            cfg.want_grad = 1
+            out = torch.zeros(lib.mmif_loss_out_doubles(B), dtype=torch.float64, device='cuda')
+            ws = torch.zeros(lib.mmif_loss_workspace_bytes(B, H, W), dtype=torch.uint8, device='cuda')
+            dU = torch.full_like(f, float('nan'))
+            L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(),
+                                             dU.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            cfg0 = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
+            up = torch.tensor([1.5, -0.25, 3.0], device='cuda')
+            dF = torch.full_like(f, float('nan'))
+            L.check(lib.mmif_fusion_loss_bwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg0), up.data_ptr(), None,
+                                             dF.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            torch.cuda.synchronize()
+            res[ws_on] = (out[:L.LOSS_HEAD + L.LOSS_PER_SAMPLE * B].clone(), dU.clone(), dF.clone())
+        (o0, u0, d0), (o1, u1, d1) = res['0'], res['1']
+        assert torch.isfinite(u1).all() and torch.isfinite(d1).all(), (B, H, W)
+        rel = ((o0 - o1).abs() / o0.abs().clamp_min(1e-12)).max().item()
+        assert rel <= 1e-6, ((B, H, W), rel)
+        for x0, x1, nm in ((u0, u1, 'single-pass'), (d0, d1, 'recomputing')):
+            err = (x0 - x1).abs().max().item() / max(x0.abs().max().item(), 1e-30)
+            assert err <= 2e-6, ((B, H, W), nm, err)
