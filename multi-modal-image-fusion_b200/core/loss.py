@@ -15,7 +15,7 @@ windows 11/9/7/5/3 on the strip kernels and for ANY other window of 2..17 taps (
 (mmif_ssim_generic_*), with a dict that is differentiable w.r.t. both images through all three entries, per-sample or as
 size_average=False maps.  'msw-ssim' runs the same forward / backward kernels with the 11/9/7/5/3 windows and per-position
 weights.  Not built (raise NotImplementedError, never a silent fallback): gradients of the fused objective w.r.t. the
-sources, SSIM windows above 17 taps, MSW_SSIM(size_average=True), MS_SSIM(size_average=False).
+sources, SSIM windows above 17 taps, MS_SSIM(size_average=False), MSW_SSIM(size_average=False) with windows other than 11/9/7/5/3.
 """
 import ctypes
 import threading
@@ -286,12 +286,12 @@ class _WeightedSSIM(torch.autograd.Function):
     SOURCE images only, so it is a per-sample constant of the backward."""
 
     @staticmethod
-    def forward(ctx, img1, img2, imgf, data_range):
+    def forward(ctx, img1, img2, imgf, data_range, win=11):
         x1, x2, y = _prep3(img1, img2, imgf)
-        ps = _fwd_per_sample(x1, x2, y, data_range).to(torch.float32)
+        ps = _fwd_per_sample(x1, x2, y, data_range, win).to(torch.float32)
         gamma = ps[:, 2] / (ps[:, 2] + ps[:, 5]).clamp_(min=eps)
         ctx.save_for_backward(x1, x2, y, gamma)
-        ctx.data_range, ctx.in_shape = data_range, imgf.shape
+        ctx.data_range, ctx.in_shape, ctx.win = data_range, imgf.shape, win
         return (gamma * ps[:, 0]).mean() + ((1.0 - gamma) * ps[:, 3]).mean()
 
     @staticmethod
@@ -299,8 +299,8 @@ class _WeightedSSIM(torch.autograd.Function):
         x1, x2, y, gamma = ctx.saved_tensors
         pw = torch.stack([gamma, 1.0 - gamma], dim=1)
         g1 = g.to(torch.float32).reshape(1).contiguous()
-        dF = _ssim_bwd_ex(x1, x2, y, ctx.data_range, g1, pw, 0, 1.0 / y.shape[0])
-        return None, None, dF.view(ctx.in_shape), None
+        dF = _ssim_bwd_ex(x1, x2, y, ctx.data_range, g1, pw, 0, 1.0 / y.shape[0], ctx.win)
+        return None, None, dF.view(ctx.in_shape), None, None
 
 
 def _loss_sigma(win):
@@ -796,12 +796,19 @@ class MSW_SSIM(nn.Module):
         self.size_average = size_average
 
     def forward(self, img1, img2, imgf):
-        if any(k not in (11, 9, 7, 5, 3) for k in self.win_sizes):
-            raise NotImplementedError('MSW_SSIM: windows 11, 9, 7, 5, 3 are built')
-        if self.size_average:
-            raise NotImplementedError('MSW_SSIM(size_average=True) (per-sample gamma from the window means) is not built; '
-                                      'SSIMLoss("msw-ssim") and the class default use size_average=False')
         dr = _auto_range(img1) if self.data_range is None else self.data_range
+        if self.size_average:
+            # size_average=True (loss.py:222-237 with per-sample dict entries): gamma_b = sigma1_b / (sigma1_b + sigma2_b) from the
+            # window-MEAN clamped variances of the sources, one weighted SSIM per window size — 'w-ssim' with that window
+            if any(not 2 <= int(k) <= 17 for k in self.win_sizes):
+                raise NotImplementedError('SSIM windows of 2..17 taps are built')
+            acc = 0.0
+            for k in self.win_sizes:
+                x1, x2, y = _pad3(img1, img2, imgf, int(k)) if self.use_padding else (img1, img2, imgf)
+                acc = acc + _WeightedSSIM.apply(x1, x2, y, dr, int(k))
+            return acc / len(self.win_sizes)
+        if any(k not in (11, 9, 7, 5, 3) for k in self.win_sizes):
+            raise NotImplementedError('MSW_SSIM(size_average=False): windows 11, 9, 7, 5, 3 are built')
         return _MSWSSIM.apply(img1, img2, imgf, dr, tuple(self.win_sizes), bool(self.use_padding))
 
 

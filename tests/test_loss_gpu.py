@@ -591,3 +591,25 @@ def test_ms_ssim_module_generic_window():
     frac, mx, where = gates.grad_report(F_.grad.cpu().numpy(), f64.grad.numpy())
     ref_err = np.abs(f32.grad.numpy() - f64.grad.numpy()).max() / np.abs(f64.grad.numpy()).max()
     assert mx <= max(1e-5, ref_err), f'max-norm err {mx:.3e} at {where} (fp32 reference: {ref_err:.3e})'
+
+
+@pytest.mark.parametrize('use_padding', [False, True])
+def test_msw_ssim_size_average_true(use_padding):
+    """MSW_SSIM(size_average=True) (loss.py:211-237 with per-sample dict entries): gamma_b from the window-mean clamped
+    variances of the sources, one weighted SSIM per window size; also with a window set the strip kernels do not cover."""
+    ML = _mods()
+    a, b, f = (T(x) for x in cases.loss_case('rand_3x64x96'))
+
+    def ref(wins):
+        def fn(x1, x2, y):
+            acc = 0.0
+            for k in wins:
+                o1 = OL.ssim(x1, y, k, None, 1.0, use_padding, size_average=True)
+                o2 = OL.ssim(x2, y, k, None, 1.0, use_padding, size_average=True)
+                gm = o1['sigma'] / (o1['sigma'] + o2['sigma']).clamp(min=1e-7)
+                acc = acc + (gm * o1['ssim']).mean() + ((1.0 - gm) * o2['ssim']).mean()
+            return acc / len(wins)
+        return fn
+
+    for wins in ((11, 9, 7, 5, 3), (13, 6)):
+        _grad_vs_oracle(lambda x1, x2, y: ML.MSW_SSIM(wins, 1.0, use_padding, size_average=True)(x1, x2, y), ref(wins), a, b, f)
