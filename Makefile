@@ -6,7 +6,7 @@ HDR := $(wildcard $(PKG)/csrc/*.cuh) include/mmif_b200.h
 OBJ := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(SRC))
 LIB := $(PKG)/libmmif_b200.so
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2 \
-           -Xptxas -v --expt-relaxed-constexpr
+           -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
 
 PYINC := $(shell python3 -c "import sysconfig; print(sysconfig.get_paths()['include'])")
 FAST := $(PKG)/_fastcall.so

@@ -34,6 +34,9 @@ constexpr int kWsNT = 512;
 #define MMIF_WS_SLEEP_NS 40
 #endif
 constexpr unsigned kWsSleepNs = MMIF_WS_SLEEP_NS;
+#ifndef MMIF_WS_H_UNROLL
+#define MMIF_WS_H_UNROLL 0
+#endif
 #ifndef MMIF_WS_V_ROLLED
 #define MMIF_WS_V_ROLLED 0
 #endif
@@ -311,7 +314,11 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
             const unsigned zm = (ZMODE && q >= i0 && q < iend) ? a_zmask : 0u;
             // two passes of four window columns through ONE copy of the code: the instruction footprint of the three
             // concurrent streams has to fit the SM's 32 KB instruction cache
+#if MMIF_WS_H_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int half = 0; half < 2; ++half) {
                 float2 ab[4], cc[4];
                 const unsigned vmh = a_vmask >> (half * 4), zmh = zm >> (half * 4);
