@@ -297,12 +297,14 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
         // =========================================================== G1: horizontal moments -> derivative coefficients
         const int ho = lane & 7, hg = warp * 4 + (lane >> 3);
         float2 z_ss = f2(0.f, 0.f), z_cs = z_ss, z_sg = z_ss;
-        unsigned a_vmask = 0u, a_zmask = 0u;
+        // bit j: the SSIM value of window column hg * 8 + j belongs to this CTA's tile (single-pass loss sums).  Window columns
+        // that do not exist (outside the image) need no mask here: G3 zeroes their vertical-adjoint output, and the columns
+        // past the strip's 118 are never read by the horizontal adjoint.
+        unsigned a_zmask = 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int pw = hg * 8 + j, pc = jw0 + kVOFF + pw;
             const bool v = (pw < kWC) && (pc >= 0) && (pc < p.Wout);
-            a_vmask |= v ? (1u << j) : 0u;
             a_zmask |= (v && pc >= j0 && pc < jend) ? (1u << j) : 0u;
         }
         for (int b = 0; b < nb; ++b) {
@@ -321,7 +323,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
 #endif
             for (int half = 0; half < 2; ++half) {
                 float2 ab[4], cc[4];
-                const unsigned vmh = a_vmask >> (half * 4), zmh = zm >> (half * 4);
+                const unsigned zmh = zm >> (half * 4);
                 if (active) {
                     float2 acc[4][4];
                     hpass<WIN, 4, false, 4>(sm.vbuf[b & 1] + ho * kVPitch + hg * 8 + half * 4, kVCols, p.taps, acc);
@@ -329,7 +331,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                     for (int j = 0; j < 4; ++j) {
                         const Moments mo = moments_of(acc[j]);
                         const Stats st = stats_from(mo, sh);
-                        const float myk = (st.vy >= 0.f) ? 1.f : 0.f;
+                        const bool vy_ok = st.vy >= 0.f;                     // clamp(min=0) passes the gradient at 0
                         const float2 vk = max2(st.vk, 0.f);
                         const float vy = fmaxf(st.vy, 0.f);
                         const float2 A1 = fma2(st.mu, bcast(2.f * st.muy), bcast(p.C1));
@@ -341,13 +343,13 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                         const float2 L = mul2(A1, R1);
                         const float2 S = mul2(L, Cs);
                         const float2 ch = mul2(L, R2);
-                        const float2 nbv = muls(myk, mul2(S, R2));
+                        const float2 sr2 = mul2(S, R2);
+                        const float2 nbv = f2(vy_ok ? sr2.x : 0.f, vy_ok ? sr2.y : 0.f);
                         float2 a = mul2(mul2(Cs, R1), fma2(L, bcast(-st.muy), st.mu));
                         a = fma2(nbv, bcast(mo.my + sh.ecy), a);
                         a = fma2(ch, fma2(mo.mk, bcast(-1.f), sh.nec), a);
-                        const bool vj = (vmh >> j) & 1u;
-                        ab[j] = vj ? f2(a.x + a.y, nbv.x + nbv.y) : f2(0.f, 0.f);
-                        cc[j] = vj ? ch : f2(0.f, 0.f);
+                        ab[j] = f2(a.x + a.y, nbv.x + nbv.y);
+                        cc[j] = ch;
                         if (ZMODE) {
                             // predicated adds (never a multiply by 0: the window columns past the strip are computed on
                             // never-written pad columns of vbuf whose stale bits can be NaN / Inf)
@@ -413,13 +415,18 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                 // two passes of four rows through one copy of the code (instruction footprint, see G1); within a pass the
                 // three stages (loads + Sobel + sign factors, neighbour exchange, vertical combination) keep four
                 // independent row chains in flight
+                // input rows Rb + 2 .. Rb + 9: six in this batch's ring slot, two in the next one; per pass two base pointers
+                // with constant row offsets instead of a wrap per row
+                const float* ps0 = s_p0 + rbase * kRPB;
+                const float* ps1 = s_p0 + ((slot + 1 == kWsSlots) ? 0 : slot + 1) * (kRB * kRPB);
 #pragma unroll 1
                 for (int h4 = 0; h4 < 2; ++h4) {
                     float tx[4], ty[4], pg[4];
+                    const float* plo = ps0 + (2 + 4 * h4) * kRPB;
+                    const float* phi = h4 ? ps1 - 2 * kRPB : plo;
 #pragma unroll
                     for (int s4 = 0; s4 < 4; ++s4) {
-                        const int lro = ws_wrap(rbase + 2 + h4 * 4 + s4) * kRPB;   // ring row of input row Rb + 2 + step
-                        const float* rp = s_p0 + lro;
+                        const float* rp = (s4 < 2 ? plo : phi) + s4 * kRPB;        // ring row of input row Rb + 2 + 4 h4 + s4
                         const float2 um = f2(rp[-1], rp[kRingImg - 1]);
                         const float2 uc = f2(rp[0], rp[kRingImg]);
                         const float2 up = f2(rp[1], rp[kRingImg + 1]);
@@ -526,6 +533,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
         // =========================================================== G3: vertical adjoint B1(b) (stateful) -> tbuf, horizontal adjoint + combine + store B2(b)
         const int ho = lane & 7, hg = warp * 4 + (lane >> 3);
         const float k_ssim2 = 2.f * g_ssim * p.ssim_base / ((float)p.Hout * (float)p.Wout);
+        const bool b1_valid = (jw0 + kVOFF + t >= 0) && (jw0 + kVOFF + t < p.Wout);      // window column t exists in the image
         float2 carry[HALO][2];
 #pragma unroll
         for (int d = 0; d < HALO; ++d) carry[d][0] = carry[d][1] = f2(0.f, 0.f);
@@ -554,10 +562,18 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                 }
                 if (b + 2 < nb) nb_arrive(NB_CEMPTY + (b & 1));
                 if (emit) {
+                    if (b1_valid) {
 #pragma unroll
-                    for (int o = 0; o < kRB; ++o) {
-                        sm.tbuf[o * kCPitch + t] = P[o][0];
-                        sm.tbuf[o * kCPitch + kTWI + t] = P[o][1];
+                        for (int o = 0; o < kRB; ++o) {
+                            sm.tbuf[o * kCPitch + t] = P[o][0];
+                            sm.tbuf[o * kCPitch + kTWI + t] = P[o][1];
+                        }
+                    } else {                      // a window column outside the image contributes nothing
+#pragma unroll
+                        for (int o = 0; o < kRB; ++o) {
+                            sm.tbuf[o * kCPitch + t] = f2(0.f, 0.f);
+                            sm.tbuf[o * kCPitch + kTWI + t] = f2(0.f, 0.f);
+                        }
                     }
                 }
 #pragma unroll
