@@ -37,7 +37,12 @@ static int bwd_tg(int win) { const int halo = win - 1; return (kTWI - 2 * halo) 
 // longest-processing-time-first list scheduling, which trims the partial last wave that costs a per-rank batch of 8
 // (304 columns on 296 CTA slots) 8 % in the uniform scheme.  Every sample and strip is cut the same way, so a sample's
 // result does not depend on its position in the batch.
-struct BwdGeom { int Hout, Wout, seg_rows, seg_short, n_tall, nseg, nstrip; };
+// Warp-specialised kernel only: the LAST fine_strips strips of every sample form a second class that is cut into short
+// segments of fine_rows rows and dispatched after everything else.  With one CTA per SM the other strips can then be
+// full-height columns in whole waves (W = 4096: 37 of the 38 strips x B columns = B / 4 waves of 148) and the fine class
+// fills the SMs up to a common finish line; every sample is still cut the same way.
+struct BwdGeom { int Hout, Wout, seg_rows, seg_short, n_tall, nseg, nstrip, fine_strips, fine_rows, nseg_fine; };
+static int geom_ctas_per_sample(const BwdGeom& g) { return (g.nstrip - g.fine_strips) * g.nseg + g.fine_strips * g.nseg_fine; }
 
 static int geom_nseg(int H, int T, int n_tall, int s) {
     const int tall_rows = n_tall * T;
@@ -100,19 +105,12 @@ static double simulate_makespan(int H, int cols, int T, int n_tall, int s, int e
 // The same for the warp-specialised kernel: ONE CTA per SM, so plain list scheduling on 148 machines.  The CTAs come in at most
 // three classes of equal length dispatched in order (tall segments, short segments, the ragged last segment), so the machines
 // are tracked as a handful of (load, count) groups: exact, and ~total / 148 steps instead of total heap operations.
-static double simulate_makespan_1(int H, int cols, int T, int n_tall, int s, int extra) {
-    constexpr int kSM = 148;
-    const int nseg = geom_nseg(H, T, n_tall, s);
+struct ListSched {             // greedy list scheduling of runs of equal jobs on 148 machines, tracked as (load, count) groups
     struct Grp { double load; int cnt; };
-    Grp grp[16];
-    int ng = 1;
-    grp[0] = Grp{0.0, kSM};
-    for (int seg = 0; seg < nseg; ++seg) {
-        int i0, i1;
-        if (seg < n_tall) { i0 = seg * T; i1 = i0 + T; } else { i0 = n_tall * T + (seg - n_tall) * s; i1 = i0 + s; }
-        if (i1 > H) i1 = H;
-        const double len = (double)(i1 - i0 + extra);
-        int n = cols;
+    Grp grp[24];
+    int ng;
+    ListSched() : ng(1) { grp[0] = Grp{0.0, 148}; }
+    void add(int n, double len) {
         while (n > 0) {
             int lo = 0;
             for (int k = 1; k < ng; ++k)
@@ -125,15 +123,31 @@ static double simulate_makespan_1(int H, int cols, int T, int n_tall, int s, int
             for (int k = 0; k < ng; ++k)
                 if (grp[k].load == nl) hit = k;
             if (hit >= 0) grp[hit].cnt += take;
-            else if (ng < 16) grp[ng++] = Grp{nl, take};
-            else { grp[0].cnt += take; if (grp[0].load < nl) grp[0].load = nl; }      // cannot happen with three classes
+            else if (ng < 24) grp[ng++] = Grp{nl, take};
+            else { grp[0].cnt += take; if (grp[0].load < nl) grp[0].load = nl; }      // cannot happen with a handful of classes
             n -= take;
         }
     }
-    double makespan = 0.0;
-    for (int k = 0; k < ng; ++k)
-        if (grp[k].cnt > 0 && grp[k].load > makespan) makespan = grp[k].load;
-    return makespan;
+    void add_segments(int H, int cols, int T, int n_tall, int s, int extra) {
+        const int nseg = geom_nseg(H, T, n_tall, s);
+        for (int seg = 0; seg < nseg; ++seg) {
+            int i0, i1;
+            if (seg < n_tall) { i0 = seg * T; i1 = i0 + T; } else { i0 = n_tall * T + (seg - n_tall) * s; i1 = i0 + s; }
+            if (i1 > H) i1 = H;
+            add(cols, (double)(i1 - i0 + extra));
+        }
+    }
+    double makespan() const {
+        double m = 0.0;
+        for (int k = 0; k < ng; ++k)
+            if (grp[k].cnt > 0 && grp[k].load > m) m = grp[k].load;
+        return m;
+    }
+};
+static double simulate_makespan_1(int H, int cols, int T, int n_tall, int s, int extra) {
+    ListSched ls;
+    ls.add_segments(H, cols, T, n_tall, s, extra);
+    return ls.makespan();
 }
 
 // ws: geometry for fusion_loss_ws_kernel (one CTA per SM) instead of fusion_loss_bwd_kernel (two)
@@ -147,6 +161,7 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     g.seg_rows = ws ? pick_seg_rows(H, B * g.nstrip, 148, extra, 0.0) : pick_seg_rows(H, B * g.nstrip, 2 * 148, extra, 0.72);
     g.seg_short = g.seg_rows; g.n_tall = ceil_div(H, g.seg_rows);
     g.nseg = g.n_tall;
+    g.fine_strips = 0; g.fine_rows = g.seg_rows; g.nseg_fine = 0;
     // memo: the search below simulates a few dozen schedules (~1 ms); a training loop asks for one shape
     struct Key { int B, H, W, win; bool ws; BwdGeom g; };
     // process-wide (the backward runs on autograd's thread and must not repeat the search) and large enough for a training
@@ -158,9 +173,11 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     std::unique_lock<std::mutex> memo_lock(memo_mu);
     const bool forced = ws && getenv("MMIF_WS_GEOM") != nullptr;
     if (forced) {                // measurement aid: MMIF_WS_GEOM="T,n_tall,s" forces the segments (tools/ws_geom_force.py)
-        int fT = 0, fn = 0, fs = 0;
-        if (sscanf(getenv("MMIF_WS_GEOM"), "%d,%d,%d", &fT, &fn, &fs) == 3 && fT >= 16 && fs >= 16 && fT % 8 == 0 && fs % 8 == 0) {
+        int fT = 0, fn = 0, fs = 0, fF = 0, fr = 0;
+        const int got = sscanf(getenv("MMIF_WS_GEOM"), "%d,%d,%d,%d,%d", &fT, &fn, &fs, &fF, &fr);
+        if (got >= 3 && fT >= 16 && fs >= 16 && fT % 8 == 0 && fs % 8 == 0) {
             g.seg_rows = fT; g.seg_short = fs; g.nseg = geom_nseg(H, fT, fn, fs); g.n_tall = fn < g.nseg ? fn : g.nseg;
+            if (got == 5 && fF >= 1 && fF < g.nstrip && fr >= 16 && fr % 8 == 0) { g.fine_strips = fF; g.fine_rows = fr; g.nseg_fine = ceil_div(H, fr); }
             return g;
         }
     }
@@ -175,22 +192,48 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     if (ws && !uniform_only) {
         // one CTA per SM: the closed-form tail term of pick_seg_rows ranks the candidates wrongly (B = 64: one 3072-row segment,
         // 17 waves, instead of two of 1536, 33 waves; measured 15.03 vs 14.86 ms), while list scheduling simulated on 148 SMs
-        // with 40 rows of per-CTA overhead reproduces every measured ordering (tools/ws_geom_scan.sh).  Full search: tall
-        // heights H / k (k = 1..24), short heights T / {1, 2, 3, 4, 6, 8}, every count of tall segments.
+        // with 40 rows of per-CTA overhead reproduces every measured ordering (tools/ws_geom_scan.sh).  Full search: the number
+        // of fine strips F (0..3), for the other strips tall heights H / k (k = 1..24), short heights T / {1, 2, 3, 4, 6, 8} and
+        // every count of tall segments, for the fine strips every height H / k down to 32 rows.
         double best = 1e300;
         const int divs[6] = {1, 2, 3, 4, 6, 8};
-        for (int k = 1; k <= 24; ++k) {
-            const int T = ceil_div(ceil_div(H, k), 8) * 8;
-            if (T < 32 && k > 1) break;
-            for (int di = 0; di < 6; ++di) {
-                const int sh = ceil_div(ceil_div(T, divs[di]), 8) * 8;
-                if (sh < 16 || (di > 0 && sh >= T)) continue;
-                const int full = ceil_div(H, T);
-                for (int nt = (di == 0 ? full : 0); nt <= full && (nt == full || nt * T < H); ++nt) {
-                    const int nseg = geom_nseg(H, T, nt, sh);
-                    if ((long long)cols * nseg > 40000) continue;
-                    const double m = simulate_makespan_1(H, cols, T, nt, sh, extra);
-                    if (m < best * (di == 0 ? 1.0 : 0.995)) { best = m; g.seg_rows = T; g.seg_short = sh; g.n_tall = nt < nseg ? nt : nseg; g.nseg = nseg; }
+        static const int max_fine = getenv("MMIF_WS_MAX_FINE") ? atoi(getenv("MMIF_WS_MAX_FINE")) : 3;
+        for (int F = 0; F <= max_fine && F < g.nstrip; ++F) {
+            const int colsA = B * (g.nstrip - F), colsF = B * F;
+            for (int k = 1; k <= 24; ++k) {
+                const int T = ceil_div(ceil_div(H, k), 8) * 8;
+                if (T < 32 && k > 1) break;
+                for (int di = 0; di < 6; ++di) {
+                    const int sh = ceil_div(ceil_div(T, divs[di]), 8) * 8;
+                    if (sh < 16 || (di > 0 && sh >= T)) continue;
+                    const int full = ceil_div(H, T);
+                    for (int nt = (di == 0 ? full : 0); nt <= full && (nt == full || nt * T < H); ++nt) {
+                        const int nseg = geom_nseg(H, T, nt, sh);
+                        if ((long long)colsA * nseg > 40000) continue;
+                        ListSched base;
+                        base.add_segments(H, colsA, T, nt, sh, extra);
+                        if (F == 0) {
+                            const double m = base.makespan();
+                            if (m < best * (di == 0 ? 1.0 : 0.995)) {
+                                best = m; g.seg_rows = T; g.seg_short = sh; g.n_tall = nt < nseg ? nt : nseg; g.nseg = nseg;
+                                g.fine_strips = 0; g.fine_rows = T; g.nseg_fine = 0;
+                            }
+                            continue;
+                        }
+                        for (int kf = 1; kf <= 96; ++kf) {
+                            const int fr = ceil_div(ceil_div(H, kf), 8) * 8;
+                            if (fr < 32) break;
+                            const int nsf = ceil_div(H, fr);
+                            if (nsf != kf || (long long)colsF * nsf > 20000) continue;
+                            ListSched ls = base;
+                            ls.add_segments(H, colsF, fr, nsf, fr, extra);
+                            const double m = ls.makespan();
+                            if (m < best * 0.99) {             // a fine class has to earn its extra halo rows
+                                best = m; g.seg_rows = T; g.seg_short = sh; g.n_tall = nt < nseg ? nt : nseg; g.nseg = nseg;
+                                g.fine_strips = F; g.fine_rows = fr; g.nseg_fine = nsf;
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -218,6 +261,8 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
     if (debug_geom)
         fprintf(stderr, "[mmif] bwd geometry%s B=%d H=%d W=%d win=%d: %d strips, %d segments = %d x %d rows + %d x %d rows\n", ws ? " (ws)" : "", B, H, W, win,
                 g.nstrip, g.nseg, g.n_tall < g.nseg ? g.n_tall : g.nseg, g.seg_rows, g.nseg > g.n_tall ? g.nseg - g.n_tall : 0, g.seg_short);
+    if (debug_geom && g.fine_strips)
+        fprintf(stderr, "[mmif]   fine class: the last %d strip(s) of every sample in %d segments of %d rows\n", g.fine_strips, g.nseg_fine, g.fine_rows);
     memo_lock.lock();
     Key& k = memo[memo_next];
     k.B = B; k.H = H; k.W = W; k.win = win; k.ws = ws; k.g = g;
@@ -234,6 +279,7 @@ struct BwdParams {
                              // gout[0] set and gout[1] / gout[2] NULL = those two terms get no gradient)
     int B, H, W, Hout, Wout;
     int seg_rows, seg_short, n_tall, nseg, nstrip;   // row segments: see BwdGeom
+    int fine_strips, fine_rows, nseg_fine;           // warp-specialised kernel: the fine class (BwdGeom)
     Taps taps;
     float C1, C2;
     int pixel_combine, grad_combine, pixel_norm, grad_norm;
@@ -727,7 +773,7 @@ static size_t loss_ws_core_bytes(int B, int H, int W) {
         best = best > z ? best : z;
         if (wins[k] == WIN11) {
             const BwdGeom gw = bwd_geom(B, H, W, WIN11, true);
-            const size_t zw = ws_counters_bytes(B) + (size_t)B * gw.nstrip * gw.nseg * 8 * sizeof(double);
+            const size_t zw = ws_counters_bytes(B) + (size_t)B * geom_ctas_per_sample(gw) * 8 * sizeof(double);
             best = best > zw ? best : zw;
         }
     }
@@ -761,6 +807,7 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     p.gout[0] = up.g[0]; p.gout[1] = up.g[1]; p.gout[2] = up.g[2];
     p.B = B; p.H = H; p.W = W; p.Hout = g.Hout; p.Wout = g.Wout;
     p.seg_rows = g.seg_rows; p.seg_short = g.seg_short; p.n_tall = g.n_tall; p.nseg = g.nseg; p.nstrip = g.nstrip;
+    p.fine_strips = g.fine_strips; p.fine_rows = g.fine_rows; p.nseg_fine = g.nseg_fine;
     make_taps(&p.taps, win, (ex && ex->win) ? ex->sigma : 1.5);
     const double L = cfg->data_range;
     p.C1 = (float)((0.01 * L) * (0.01 * L)); p.C2 = (float)((0.03 * L) * (0.03 * L));
@@ -830,8 +877,9 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         }
     } else if (use_ws) {
         const size_t smw = sizeof(SmemWS);
-        if (zmode) fusion_loss_ws_kernel<11, true, true><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
-        else fusion_loss_ws_kernel<11, true, false><<<grid, kWsNT, smw, st>>>(m1, m2, my, p);
+        const dim3 gridw((unsigned)((size_t)B * geom_ctas_per_sample(g)));       // linear: class by class, segment by segment
+        if (zmode) fusion_loss_ws_kernel<11, true, true><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+        else fusion_loss_ws_kernel<11, true, false><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
     } else if (zmode) {
         if (fast) fusion_loss_bwd_kernel<11, true, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
         else fusion_loss_bwd_kernel<11, false, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);

@@ -34,6 +34,9 @@ constexpr int kWsNT = 512;
 #define MMIF_WS_SLEEP_NS 40
 #endif
 constexpr unsigned kWsSleepNs = MMIF_WS_SLEEP_NS;
+#ifndef MMIF_WS_NO_SFAST
+#define MMIF_WS_NO_SFAST 0
+#endif
 #ifndef MMIF_WS_H_UNROLL
 #define MMIF_WS_H_UNROLL 0
 #endif
@@ -145,10 +148,33 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
     if (!ZMODE && p.dF_unit != nullptr && g_ssim == g_pix && g_pix == g_grad) return;     // rescale_unit_kernel did the work
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemWS& sm = *reinterpret_cast<SmemWS*>(smem_raw);
-    const int strip = blockIdx.x, n = blockIdx.y, seg = blockIdx.z;
+    // Linear CTA index -> (class, segment, sample, strip).  Dispatch order = launch order: all tall segments of the coarse
+    // strips, then their short segments, then the fine class (the last fine_strips strips of every sample in segments of
+    // fine_rows rows): longest jobs first, the fine ones level the SMs at the end.
+    const int sa = p.nstrip - p.fine_strips;              // coarse strips per sample
+    const int cols_a = p.B * sa, n_a = cols_a * p.nseg;
+    int id = blockIdx.x, seg, strip, n, i0, seg_h, blk;
+    if (id < n_a) {
+        seg = id / cols_a;
+        const int lin = id - seg * cols_a;
+        n = lin / sa;
+        strip = lin - n * sa;
+        i0 = (seg < p.n_tall) ? seg * p.seg_rows : p.n_tall * p.seg_rows + (seg - p.n_tall) * p.seg_short;
+        seg_h = (seg < p.n_tall) ? p.seg_rows : p.seg_short;
+        blk = seg * sa + strip;
+    } else {
+        id -= n_a;
+        const int cols_f = p.B * p.fine_strips;
+        seg = id / cols_f;
+        const int lin = id - seg * cols_f;
+        n = lin / p.fine_strips;
+        strip = sa + (lin - n * p.fine_strips);
+        i0 = seg * p.fine_rows;
+        seg_h = p.fine_rows;
+        blk = sa * p.nseg + seg * p.fine_strips + (strip - sa);
+    }
+    const int nblk = sa * p.nseg + p.fine_strips * p.nseg_fine;
     const int j0 = strip * kTG;
-    const int i0 = (seg < p.n_tall) ? seg * p.seg_rows : p.n_tall * p.seg_rows + (seg - p.n_tall) * p.seg_short;
-    const int seg_h = (seg < p.n_tall) ? p.seg_rows : p.seg_short;
     const int jw0 = j0 - kOFF;
     const int R0 = i0 - HALO;
     const int iend = min(i0 + seg_h, p.H);
@@ -410,7 +436,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
             const int rbase = slot * kRB;               // ring row of input row Rb
             if (b >= 2) nb_sync(NB_GEMPTY + (b & 1));             // B2(b - 2) has read this gbuf slot
             float (*gb)[kTMC + 4] = sm.gbuf[b & 1];
-            const bool s_fast = FAST && s_strip_int && (Rb >= max(2, i0)) && (Rb + 9 <= min(iend, p.H - 1));
+            const bool s_fast = !MMIF_WS_NO_SFAST && FAST && s_strip_int && (Rb >= max(2, i0)) && (Rb + 9 <= min(iend, p.H - 1));
             if (s_fast) {
                 // two passes of four rows through one copy of the code (instruction footprint, see G1); within a pass the
                 // three stages (loads + Sobel + sign factors, neighbour exchange, vertical combination) keep four
@@ -631,7 +657,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
             slot = (slot + 1 == kWsSlots) ? 0 : slot + 1;
         }
     }
-    if (ZMODE) cta_finish<kWsNT>(p.fin, zv, sm.red, &sm.flag, n, seg * p.nstrip + strip, p.nstrip * p.nseg);
+    if (ZMODE) cta_finish<kWsNT>(p.fin, zv, sm.red, &sm.flag, n, blk, nblk);
 }
 
 }  // namespace mmif
