@@ -203,7 +203,7 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
             for (int k = 1; k <= 24; ++k) {
                 const int T = ceil_div(ceil_div(H, k), 8) * 8;
                 if (T < 32 && k > 1) break;
-                for (int di = 0; di < 6; ++di) {
+                for (int di = 0; di < (F == 0 ? 6 : 1); ++di) {     // with a fine class the coarse strips stay uniform: it balances
                     const int sh = ceil_div(ceil_div(T, divs[di]), 8) * 8;
                     if (sh < 16 || (di > 0 && sh >= T)) continue;
                     const int full = ceil_div(H, T);
@@ -237,7 +237,9 @@ static BwdGeom bwd_geom(int B, int H, int W, int win = WIN11, bool ws = false) {
                 }
             }
         }
-    } else if (!uniform_only && (long long)cols * g.nseg <= 40000 && g.seg_rows >= 32) {
+    } else if (!uniform_only && win == WIN11 && (long long)cols * g.nseg <= 40000 && g.seg_rows >= 32) {
+        // (the extended SSIM-only launches with the 9/7/5/3-tap windows keep the closed-form uniform segments: their geometry is
+        // also computed for every workspace sizing, and the event simulation below costs tens of milliseconds per window)
         double best = simulate(g.seg_rows, g.n_tall, g.seg_rows);
         const BwdGeom uni = g;
         const int talls[4] = {uni.seg_rows, (uni.seg_rows * 5 / 4 + 7) / 8 * 8, (uni.seg_rows * 3 / 2 + 7) / 8 * 8, uni.seg_rows * 2};
