@@ -799,9 +799,11 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     const bool ws_off = ws_env != nullptr && atoi(ws_env) == 0;
     const bool fast = cfg->pixel_combine == MMIF_COMBINE_MAX && cfg->grad_combine == MMIF_COMBINE_MAX &&
                       cfg->pixel_norm == MMIF_NORM_L1 && cfg->grad_norm == MMIF_NORM_L1;
-    // (the other combine / norm modes run the general Sobel path on every batch: one long dependency chain per row, which a
-    // single warp group cannot hide — measured 3.45 vs 2.85 ms at 8x3072x4096 — so they stay on the 2-CTA kernel)
-    const bool use_ws = !ex && win == WIN11 && fast && !ws_off;
+    // (the other combine / norm modes run the general Sobel path with two norm derivatives per pixel on every batch; that makes
+    // the Sobel group the longest pipeline stage: measured 22.6 vs 20.9 ms at 64x3072x4096, 2.79 vs 2.73 ms at 8x — although
+    // 58 vs 65 us at 1x1024x1224 — so they stay on the 2-CTA kernel; MMIF_WS_ALL_MODES=1 puts them on the warp-specialised one)
+    static const bool ws_all_modes = getenv("MMIF_WS_ALL_MODES") != nullptr;      // measurement aid
+    const bool use_ws = !ex && win == WIN11 && (fast || ws_all_modes) && !ws_off;
     const BwdGeom g = bwd_geom(B, H, W, win, use_ws);
     BwdParams p;
     memset(&p, 0, sizeof(p));
@@ -854,6 +856,8 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         const int szw = (int)sizeof(SmemWS);
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, false>, at, szw));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, true>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, false>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, true>, at, szw));
     }
     dim3 grid(g.nstrip, B, g.nseg);
     if (!zmode && dF_unit) {
@@ -880,8 +884,13 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     } else if (use_ws) {
         const size_t smw = sizeof(SmemWS);
         const dim3 gridw((unsigned)((size_t)B * geom_ctas_per_sample(g)));       // linear: class by class, segment by segment
-        if (zmode) fusion_loss_ws_kernel<11, true, true><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
-        else fusion_loss_ws_kernel<11, true, false><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+        if (zmode) {
+            if (fast) fusion_loss_ws_kernel<11, true, true><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+            else fusion_loss_ws_kernel<11, false, true><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+        } else {
+            if (fast) fusion_loss_ws_kernel<11, true, false><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+            else fusion_loss_ws_kernel<11, false, false><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+        }
     } else if (zmode) {
         if (fast) fusion_loss_bwd_kernel<11, true, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
         else fusion_loss_bwd_kernel<11, false, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);

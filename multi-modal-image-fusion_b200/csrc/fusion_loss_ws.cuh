@@ -494,7 +494,7 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                     }
                 }
             } else {
-#pragma unroll 2
+#pragma unroll 4
                 for (int step = 0; step < kRB; ++step) {
                     const int qp = Rb + 2 + step;
                     int rr = (qp < 0) ? -qp : ((qp >= p.H) ? 2 * p.H - 2 - qp : qp);
