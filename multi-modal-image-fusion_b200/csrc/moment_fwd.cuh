@@ -325,8 +325,10 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
                         gg[k] = g;
                     }
                     const bool pick1 = gg[0] < gg[1];
-                    lp[0].mul(vj ? fn[0] : 1.0); lp[1].mul(vj ? fd[0] : 1.0); lp[2].mul(vj ? fn[1] : 1.0); lp[3].mul(vj ? fd[1] : 1.0);
-                    lp[4].mul(vj ? (pick1 ? fn[0] : fn[1]) : 1.0); lp[5].mul(vj ? (pick1 ? fd[0] : fd[1]) : 1.0);
+                    if (vj) {        // predicated multiplies (a column past the last window contributes the factor 1)
+                        lp[0].mul(fn[0]); lp[1].mul(fd[0]); lp[2].mul(fn[1]); lp[3].mul(fd[1]);
+                        lp[4].mul(pick1 ? fn[0] : fn[1]); lp[5].mul(pick1 ? fd[0] : fd[1]);
+                    }
                 } else {
                     const float2 A1 = fma2(st.mu, bcast(2.f * st.muy), bcast(p.C1));
                     const float2 B1 = fma2(st.mu, st.mu, bcast(fmaf(st.muy, st.muy, p.C1)));
@@ -348,10 +350,10 @@ moment_fwd_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constan
                             if (p.maps[4]) p.maps[4][o] = CS.y;
                             if (p.maps[5]) p.maps[5][o] = SG.y;
                         }
-                    } else {
-                        s0 = add2(s0, f2(vj ? S.x : 0.f, vj ? S.y : 0.f));
-                        s1 = add2(s1, f2(vj ? CS.x : 0.f, vj ? CS.y : 0.f));
-                        s2 = add2(s2, f2(vj ? SG.x : 0.f, vj ? SG.y : 0.f));
+                    } else if (vj) {          // predicated adds instead of six selects per column
+                        s0 = add2(s0, S);
+                        s1 = add2(s1, CS);
+                        s2 = add2(s2, SG);
                     }
                 }
             }

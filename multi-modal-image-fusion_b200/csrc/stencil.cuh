@@ -170,12 +170,19 @@ __device__ __forceinline__ void vpass_moments(SM& sm, const Taps& tp, const Shif
     const int t = threadIdx.x, tr = t + coff;
     float2 acc[kRB][4];
     const float2 negc = f2(-h.c.x, -h.c.y);
+    // the kRB + WIN - 1 input rows lie in consecutive 8-row ring slots: one base pointer per slot, constant row offsets inside
+    // it (no wrap arithmetic per row: every instruction costs a dispatch-port cycle)
+    constexpr int kSeg = (kRB + WIN - 1 + kRB - 1) / kRB;
+    constexpr int kPlane = SM::kRows * SM::kPitch;
+    const float* seg[kSeg];
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) seg[k] = &sm.ring[0][SM::wrap(base + k * kRB)][tr];
 #pragma unroll
     for (int rr = 0; rr < kRB + WIN - 1; ++rr) {
-        const int lr = SM::wrap(base + rr);
-        const float y = sm.ring[2][lr][tr] - h.cy;
+        const float* rp = seg[rr / kRB] + (rr % kRB) * SM::kPitch;
+        const float y = rp[2 * kPlane] - h.cy;
         float2 P[4];
-        P[0] = add2(f2(sm.ring[0][lr][tr], sm.ring[1][lr][tr]), negc);
+        P[0] = add2(f2(rp[0], rp[kPlane]), negc);
         P[1] = mul2(P[0], P[0]);
         P[2] = muls(y, P[0]);
         P[3] = f2(y, y * y);
