@@ -195,45 +195,49 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
         mbar_fence_init();
     }
     __syncthreads();
+    // the first three ring groups are requested BEFORE the tile shift is sampled (two CTA barriers and a dependent global load):
+    // their latency is the longest item of a short CTA's prologue
+    auto issue = [&](int g) {               // input rows R0 + 8 g .. + 8 of the three images -> ring slot g % kWsSlots
+        const int slot = g % kWsSlots;
+        const uint32_t par = ((g / kWsSlots) & 1) ^ 1;
+        if (use_tma) {
+            if (t == 0) {
+                mbar_wait_wd(&sm.ring_empty[slot], par);
+                uint64_t* bar = (uint64_t*)&sm.ring_full[slot];
+                mbar_expect_tx(bar, kWsGroupBytes);
+                tma_load_3d(&sm.ring[0][slot * kRB][0], &map1, jw0, R0 + g * kRB, n, bar);
+                tma_load_3d(&sm.ring[1][slot * kRB][0], &map2, jw0, R0 + g * kRB, n, bar);
+                tma_load_3d(&sm.ring[2][slot * kRB][0], &mapy, jw0, R0 + g * kRB, n, bar);
+            }
+        } else {
+            mbar_wait_wd(&sm.ring_empty[slot], par);
+            for (int tc = t; tc < kRPB; tc += 128) {
+                const int col = jw0 + tc;
+                const bool cok = (col >= 0) && (col < p.W);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int r = 0; r < kRB; ++r) {
+                        const int row = R0 + g * kRB + r;
+                        float v = 0.f;
+                        if (cok && row >= 0 && row < p.H) v = __ldg(img[k] + (size_t)row * p.W + col);
+                        sm.ring[k][slot * kRB + r][tc] = v;
+                    }
+                }
+            }
+            mbar_arrive_each(&sm.ring_full[slot]);
+        }
+    };
+    if (grp == 0) {
+        issue(0);
+        issue(1);
+        issue(2);
+    }
     const Shift sh = tile_shift_ws(sm.shift_scratch, img[0], img[1], img[2], p.H, p.W, R0, iend - R0 + HALO, jw0, p.taps);
     double zv[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 
     if (grp == 0) {
         // =========================================================== G0: input ring (TMA producer), vertical moments
-        auto issue = [&](int g) {               // input rows R0 + 8 g .. + 8 of the three images -> ring slot g % kWsSlots
-            const int slot = g % kWsSlots;
-            const uint32_t par = ((g / kWsSlots) & 1) ^ 1;
-            if (use_tma) {
-                if (t == 0) {
-                    mbar_wait_wd(&sm.ring_empty[slot], par);
-                    uint64_t* bar = (uint64_t*)&sm.ring_full[slot];
-                    mbar_expect_tx(bar, kWsGroupBytes);
-                    tma_load_3d(&sm.ring[0][slot * kRB][0], &map1, jw0, R0 + g * kRB, n, bar);
-                    tma_load_3d(&sm.ring[1][slot * kRB][0], &map2, jw0, R0 + g * kRB, n, bar);
-                    tma_load_3d(&sm.ring[2][slot * kRB][0], &mapy, jw0, R0 + g * kRB, n, bar);
-                }
-            } else {
-                mbar_wait_wd(&sm.ring_empty[slot], par);
-                for (int tc = t; tc < kRPB; tc += 128) {
-                    const int col = jw0 + tc;
-                    const bool cok = (col >= 0) && (col < p.W);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-                        for (int r = 0; r < kRB; ++r) {
-                            const int row = R0 + g * kRB + r;
-                            float v = 0.f;
-                            if (cok && row >= 0 && row < p.H) v = __ldg(img[k] + (size_t)row * p.W + col);
-                            sm.ring[k][slot * kRB + r][tc] = v;
-                        }
-                    }
-                }
-                mbar_arrive_each(&sm.ring_full[slot]);
-            }
-        };
-        issue(0);
-        issue(1);
-        issue(2);
         mbar_wait_wd(&sm.ring_full[0], 0);
         mbar_wait_wd(&sm.ring_full[1], 0);
 
