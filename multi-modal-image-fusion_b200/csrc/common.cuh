@@ -62,7 +62,13 @@ void make_taps(Taps* t, int win, double sigma);
 // (tools/microbench/pipes.cu): FFMA 123 op/clk/SM, FFMA2 58 instr/clk/SM (= 117 fma/clk/SM), so
 // packing does not raise the FMA roof but halves the issue slots the blur needs, leaving room for
 // the LDS/ALU/MUFU work of the same warp.
+#ifndef MMIF_SCALAR_FMA
+#define MMIF_SCALAR_FMA 0
+#endif
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#if MMIF_SCALAR_FMA      // measurement aid: two scalar FFMA instead of one packed FFMA2 (tools/microbench/dispatch.cu: 2 x 1.03 vs 2.22 port cycles)
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
     float2 d;
     asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
         "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
