@@ -7,8 +7,9 @@
 Workload (BASELINE.json configs[4], the configuration the headline metric is quoted on):
 fused loss forward+backward (SSIM + 0.01*pixel-max-L1 + 0.1*Sobel-max-L1, train.py:302-317) on
 synthetic 4096x3072 pairs, global batch 64 sharded by batch over the N ranks (strong scaling, the
-partition of train.py:209); one step = one forward launch + one backward launch over the rank's
-shard + one 16-byte all-reduce of the loss scalars (N > 1).  Prints ONE JSON line on rank 0.
+partition of train.py:209); one step = the three drop-in loss modules + total.backward() on the rank's shard
+(ONE launch of the warp-specialised single-pass loss + gradient kernel and the in-place rescale) + one 16-byte
+all-reduce of the loss scalars (N > 1).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
