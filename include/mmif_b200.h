@@ -94,6 +94,11 @@ enum {
 /* out[i] = counter i for i < n (HOST memory). */
 int mmif_launch_counts(unsigned long long* out, int n);
 
+/* Diagnostic (host only, no launch): how the loss + gradient kernels cut a (B, H, W) problem into CTAs.  kernel = 0: the
+ * 2-CTA kernel, 1: the warp-specialised kernel.  out[10] = {nstrip, nseg, n_tall, seg_rows, seg_short, fine_strips, fine_rows,
+ * nseg_fine, CTAs per sample, gradient columns per strip}; the tests check that every (row, column) is owned exactly once. */
+int mmif_loss_geometry(int B, int H, int W, int kernel, int* out10);
+
 int mmif_version(void);
 const char* mmif_last_error(void);
 /* 0 if device `dev` is usable by this library (compute capability 10.x). */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmmif_b200.so')
 SYMBOLS = [
     'mmif_version', 'mmif_last_error', 'mmif_check_device', 'mmif_set_gaussian_taps',
     'mmif_loss_workspace_bytes', 'mmif_loss_out_doubles', 'mmif_fusion_loss_fwd', 'mmif_fusion_loss_bwd',
-    'mmif_fusion_loss_bwd3', 'mmif_launch_counts', 'mmif_ssim_generic_workspace_bytes', 'mmif_ssim_generic_coef_doubles',
+    'mmif_fusion_loss_bwd3', 'mmif_launch_counts', 'mmif_loss_geometry', 'mmif_ssim_generic_workspace_bytes', 'mmif_ssim_generic_coef_doubles',
     'mmif_ssim_generic_fwd', 'mmif_ssim_generic_bwd',
     'mmif_tv_loss', 'mmif_tv_loss_bwd', 'mmif_ssim_bwd_ex', 'mmif_ssim_fwd_win', 'mmif_ssim_bwd_ex_win', 'mmif_mswssim_fwd', 'mmif_mswssim_bwd', 'mmif_halve', 'mmif_halve_bwd', 'mmif_reflect_pad',
     'mmif_reflect_pad_bwd', 'mmif_metric_workspace_bytes', 'mmif_stats', 'mmif_hist', 'mmif_qabf', 'mmif_qabf_raw', 'mmif_ssim',
@@ -64,6 +64,7 @@ def load():
     lib.mmif_fusion_loss_bwd.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, sz, vp]
     lib.mmif_fusion_loss_bwd3.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(MmifLossCfg), vp, vp, vp, vp, vp, vp, sz, vp]
     lib.mmif_launch_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ci]
+    lib.mmif_loss_geometry.argtypes = [ci, ci, ci, ci, ctypes.POINTER(ci)]
     lib.mmif_ssim_generic_workspace_bytes.restype = sz
     lib.mmif_ssim_generic_workspace_bytes.argtypes = [ci, ci, ci, ci]
     lib.mmif_ssim_generic_coef_doubles.restype = sz

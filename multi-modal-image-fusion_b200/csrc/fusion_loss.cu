@@ -785,6 +785,15 @@ extern "C" size_t mmif_loss_workspace_bytes(int B, int H, int W) {
     const size_t f = loss_ws_core_bytes(B, H, W);
     return f ? f + (size_t)B * 8 * sizeof(double) : 0;
 }
+extern "C" int mmif_loss_geometry(int B, int H, int W, int kernel, int* out10) {
+    if (!out10) { set_error("null out"); return MMIF_E_NULL; }
+    if (B < 1 || H < WIN11 || W < WIN11) { set_error("shape (%d,%d,%d): need B>=1 and H,W >= %d", B, H, W, WIN11); return MMIF_E_SHAPE; }
+    const BwdGeom g = bwd_geom(B, H, W, WIN11, kernel != 0);
+    const int v[10] = {g.nstrip, g.nseg, g.n_tall, g.seg_rows, g.seg_short, g.fine_strips, g.fine_rows, g.nseg_fine,
+                       kernel != 0 ? geom_ctas_per_sample(g) : g.nstrip * g.nseg, bwd_tg(WIN11)};
+    for (int i = 0; i < 10; ++i) out10[i] = v[i];
+    return MMIF_OK;
+}
 extern "C" size_t mmif_loss_out_doubles(int B) { const size_t nd = loss_block_doubles(B); return nd + (nd + 1) / 2; }
 
 struct BwdExtra { const float* pair_w; float ssim_base; int cs_only; int do_sobel; bool use_base; int win; double sigma; int msw; int accum; };

@@ -208,3 +208,39 @@ def test_fastcall_binding_loads_and_validates_without_gpu():
     assert rc_fast == rc_ct != 0
     with pytest.raises(TypeError):
         fc.loss_fwd(1, 2, 3)
+
+
+def test_loss_geometry_owns_every_row_and_column_exactly_once():
+    """Host-side check of the row-segment search (no GPU): for a sweep of shapes, decoding every CTA index the way the kernels
+    do (two-level tall / short segments; for the warp-specialised kernel also the fine class of the last strips) must
+    cover each (gradient row, gradient column) of a sample exactly once, with the CTA count the workspace is sized for."""
+    import ctypes
+    import numpy as np
+    import mmif_b200  # noqa: F401
+    from mmif_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.RandomState(5)
+    shapes = [(1, 11, 11), (2, 96, 160), (8, 256, 256), (1, 1024, 1224), (3, 517, 1030), (8, 3072, 4096), (64, 3072, 4096),
+              (5, 2000, 109), (1, 4000, 6000), (7, 333, 5000)]
+    shapes += [(int(rng.randint(1, 33)), int(rng.randint(11, 3000)), int(rng.randint(11, 5000))) for _ in range(40)]
+    for (B, H, W) in shapes:
+        for kernel in (0, 1):
+            out = (ctypes.c_int * 10)()
+            L.check(lib.mmif_loss_geometry(B, H, W, kernel, out))
+            nstrip, nseg, n_tall, T, s, F, fr, nsf, ctas, tg = list(out)
+            assert nstrip == -(-W // tg) and 0 <= F < max(nstrip, 1) and (kernel == 1 or F == 0)
+            assert ctas == (nstrip - F) * nseg + F * nsf
+            rows = np.zeros(H, dtype=np.int32)
+            for seg in range(nseg):                                   # coarse strips: tall segments first, then short ones
+                i0 = seg * T if seg < n_tall else n_tall * T + (seg - n_tall) * s
+                h = T if seg < n_tall else s
+                assert i0 < H, (B, H, W, kernel, list(out))           # no empty CTA
+                rows[i0:min(i0 + h, H)] += 1
+            assert (rows == 1).all(), (B, H, W, kernel, list(out))
+            if F:
+                rows[:] = 0
+                for seg in range(nsf):
+                    assert seg * fr < H
+                    rows[seg * fr:min(seg * fr + fr, H)] += 1
+                assert (rows == 1).all(), (B, H, W, kernel, list(out))
+            assert T % 8 == 0 and s % 8 == 0 and (F == 0 or fr % 8 == 0)
