@@ -208,7 +208,7 @@ def main():
         y = f.detach().requires_grad_(True)              # a fresh imgf every step, as the network produces one
         if ev:
             ev[0].record()
-        l1 = fn1(a, b, y)                                # launches fusion_loss_ws_kernel<11,1,1>: loss values + d(total)/d imgf
+        l1 = fn1(a, b, y)                                # launches fusion_loss_ws_kernel<11,1,2>: loss values + d(total)/d imgf
         if ev:
             ev[1].record()
         total = l1 + fn2(a, b, y, mode='max') + fn3(a, b, y, mode='max')      # the other two read the same launch
@@ -305,7 +305,7 @@ def main():
         traffic_src = 'stored constant: ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel (%s), per pixel x the pixels of one launch; not measured in this run' % ent.get('capture', 'profiles/traffic.json')
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_ws_kernel<11, FAST=1, ZMODE=1> (warp-specialised: loss values + dIf, one launch) as launched by core.loss.SSIMLoss',
+    roofline = {'bound': 'hbm', 'kernel': 'fusion_loss_ws_kernel<11, FAST=1, ZMODE=2> (warp-specialised: the three loss values + dIf, one launch) as launched by core.loss.SSIMLoss',
                 'achieved': gbs(ALG_BYTES_BWD, ms_z), 'peak': peak, 'unit': 'GB/s', 'frac': gbs(ALG_BYTES_BWD, ms_z) / peak,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'algorithmic_bytes_per_pixel': ALG_BYTES_BWD,
                 'ms_per_launch': ms_z,

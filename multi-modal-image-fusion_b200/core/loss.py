@@ -49,7 +49,7 @@ def _cfg_ref(cfg_key, want_grad):
     hit = _cfg_structs.get(k)
     if hit is None:
         c = _cfg(*cfg_key)
-        c.want_grad = 1 if want_grad else 0
+        c.want_grad = 2 if want_grad else 0       # 2: the modules read the three loss values only (include/mmif_b200.h)
         hit = _cfg_structs[k] = (c, ctypes.byref(c), ctypes.addressof(c))
         if len(_cfg_structs) > 256:
             _cfg_structs.pop(next(iter(_cfg_structs)))

@@ -800,7 +800,7 @@ struct BwdExtra { const float* pair_w; float ssim_base; int cs_only; int do_sobe
 
 struct Upstream { const float* g[3]; };
 static int launch_bwd(const float* i1, const float* i2, const float* f, int B, int H, int W, const MmifLossCfg* cfg,
-                      const Upstream& up, const float* dF_unit, float* dF, bool zmode, double* out, void* ws, size_t ws_bytes,
+                      const Upstream& up, const float* dF_unit, float* dF, int zmode, double* out, void* ws, size_t ws_bytes,
                       cudaStream_t st, const BwdExtra* ex = nullptr) {
     const int win = (ex && ex->win) ? ex->win : WIN11;
     // the training objective runs on the warp-specialised kernel; MMIF_LOSS_WS=0 is the A/B switch back to the 2-CTA kernel
@@ -863,10 +863,11 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<5, false, false, true>, at, sz));
         MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_bwd_kernel<3, false, false, true>, at, sz));
         const int szw = (int)sizeof(SmemWS);
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, false>, at, szw));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, true>, at, szw));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, false>, at, szw));
-        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, true>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, 0>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, 1>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, true, 2>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, 0>, at, szw));
+        MMIF_CUDA(cudaFuncSetAttribute(fusion_loss_ws_kernel<11, false, 1>, at, szw));
     }
     dim3 grid(g.nstrip, B, g.nseg);
     if (!zmode && dF_unit) {
@@ -893,12 +894,13 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     } else if (use_ws) {
         const size_t smw = sizeof(SmemWS);
         const dim3 gridw((unsigned)((size_t)B * geom_ctas_per_sample(g)));       // linear: class by class, segment by segment
-        if (zmode) {
-            if (fast) fusion_loss_ws_kernel<11, true, true><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
-            else fusion_loss_ws_kernel<11, false, true><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+        if (zmode == 2 && fast) fusion_loss_ws_kernel<11, true, 2><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+        else if (zmode) {
+            if (fast) fusion_loss_ws_kernel<11, true, 1><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+            else fusion_loss_ws_kernel<11, false, 1><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
         } else {
-            if (fast) fusion_loss_ws_kernel<11, true, false><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
-            else fusion_loss_ws_kernel<11, false, false><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+            if (fast) fusion_loss_ws_kernel<11, true, 0><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
+            else fusion_loss_ws_kernel<11, false, 0><<<gridw, kWsNT, smw, st>>>(m1, m2, my, p);
         }
     } else if (zmode) {
         if (fast) fusion_loss_bwd_kernel<11, true, true, false><<<grid, kNT, sm, st>>>(m1, m2, my, p);
@@ -924,8 +926,8 @@ extern "C" int mmif_fusion_loss_fwd(const float* i1, const float* i2, const floa
     if (cfg->want_grad) {
         if (!dF_unit) { set_error("want_grad needs dF_unit"); return MMIF_E_NULL; }
         if (((uintptr_t)dF_unit) & 3) { set_error("dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
-        return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{nullptr, nullptr, nullptr}}, nullptr, dF_unit, true, out, ws, ws_bytes,
-                          (cudaStream_t)stream);
+        return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{nullptr, nullptr, nullptr}}, nullptr, dF_unit, cfg->want_grad == 2 ? 2 : 1, out,
+                          ws, ws_bytes, (cudaStream_t)stream);
     }
     const size_t core = loss_ws_core_bytes(B, H, W);
     FwdLaunch L;
@@ -945,7 +947,7 @@ extern "C" int mmif_fusion_loss_bwd(const float* i1, const float* i2, const floa
     if (rc) return rc;
     if (!gout3 || !dF) { set_error("null gout3/dF"); return MMIF_E_NULL; }
     if ((((uintptr_t)dF) | ((uintptr_t)dF_unit)) & 3) { set_error("dF / dF_unit must be 4-byte aligned"); return MMIF_E_ALIGN; }
-    return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{gout3, gout3 + 1, gout3 + 2}}, dF_unit, dF, false, nullptr, ws, ws_bytes,
+    return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{gout3, gout3 + 1, gout3 + 2}}, dF_unit, dF, 0, nullptr, ws, ws_bytes,
                       (cudaStream_t)stream);
 }
 
@@ -964,7 +966,7 @@ extern "C" int mmif_fusion_loss_bwd3(const float* i1, const float* i2, const flo
         set_error("dF / dF_unit / upstream gradients must be 4-byte aligned");
         return MMIF_E_ALIGN;
     }
-    return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{g_ssim, g_pixel, g_grad}}, dF_unit, dF, false, nullptr, ws, ws_bytes,
+    return launch_bwd(i1, i2, f, B, H, W, cfg, Upstream{{g_ssim, g_pixel, g_grad}}, dF_unit, dF, 0, nullptr, ws, ws_bytes,
                       (cudaStream_t)stream);
 }
 
@@ -1002,7 +1004,7 @@ extern "C" int mmif_ssim_bwd_ex_win(const float* i1, const float* i2, const floa
     memset(&ex, 0, sizeof(ex));
     ex.pair_w = pair_w; ex.ssim_base = scale; ex.cs_only = cs_only; ex.do_sobel = 0; ex.use_base = true;
     if (win != WIN11) { ex.win = win; ex.sigma = loss_sigma_of(win); }
-    return launch_bwd(i1, i2, f, B, H, W, &cfg, Upstream{{gout1, nullptr, nullptr}}, nullptr, dF, false, nullptr, ws, ws_bytes,
+    return launch_bwd(i1, i2, f, B, H, W, &cfg, Upstream{{gout1, nullptr, nullptr}}, nullptr, dF, 0, nullptr, ws, ws_bytes,
                       (cudaStream_t)stream, &ex);
 }
 
@@ -1093,6 +1095,6 @@ extern "C" int mmif_mswssim_bwd(const float* i1, const float* i2, const float* f
     BwdExtra ex;
     memset(&ex, 0, sizeof(ex));
     ex.ssim_base = scale; ex.use_base = true; ex.win = win; ex.sigma = loss_sigma_of(win); ex.msw = 1; ex.accum = accumulate;
-    return launch_bwd(i1, i2, f, B, H, W, &cfg, Upstream{{gout1, nullptr, nullptr}}, nullptr, dF, false, nullptr, ws, ws_bytes,
+    return launch_bwd(i1, i2, f, B, H, W, &cfg, Upstream{{gout1, nullptr, nullptr}}, nullptr, dF, 0, nullptr, ws, ws_bytes,
                       (cudaStream_t)stream, &ex);
 }

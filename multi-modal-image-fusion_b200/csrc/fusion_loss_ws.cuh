@@ -136,7 +136,9 @@ __device__ __forceinline__ Shift tile_shift_ws(float* scratch, const float* x1, 
     return make_shift(c3[0], c3[1], c3[2], tp.wsum, tp.weps, tp.wrho);
 }
 
-template <int WIN, bool FAST, bool ZMODE>
+// ZMODE: 0 = gradient only, 1 = gradient + all loss sums (per-sample ssim / cs / sigma means, pixel, grad), 2 = gradient + the sums
+// the training objective consumes (ssim, pixel, grad; the cs / sigma entries of the per-sample block are written as 0).
+template <int WIN, bool FAST, int ZMODE>
 __global__ void __launch_bounds__(kWsNT, 1)
 fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                       const __grid_constant__ CUtensorMap mapy, const BwdParams p) {
@@ -385,8 +387,10 @@ fusion_loss_ws_kernel(const __grid_constant__ CUtensorMap map1, const __grid_con
                             // never-written pad columns of vbuf whose stale bits can be NaN / Inf)
                             if ((zmh >> j) & 1u) {
                                 z_ss = add2(z_ss, S);
-                                z_cs = add2(z_cs, Cs);
-                                z_sg = add2(z_sg, max2(vk, 1e-4f));
+                                if (ZMODE == 1) {               // ZMODE 2: the training objective reads the SSIM means only
+                                    z_cs = add2(z_cs, Cs);
+                                    z_sg = add2(z_sg, max2(vk, 1e-4f));
+                                }
                             }
                         }
                     }

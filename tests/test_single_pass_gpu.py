@@ -283,7 +283,8 @@ def test_kernel_names_seen_by_cupti():
         pytest.skip('CUPTI recorded no kernels')
     # the single-pass instantiation: the warp-specialised kernel <11, FAST, ZMODE> (or, with MMIF_LOSS_WS=0, the 2-CTA kernel)
     norm = [n.replace('(bool)1', 'true').replace('(bool)0', 'false').replace('(bool)', '') for n in names]
-    assert any('fusion_loss_ws_kernel<11, true, true>' in n or ('fusion_loss_ws_kernel' in n and '1, 1>' in n)
+    norm = [n.replace('(int)', '') for n in norm]
+    assert any('fusion_loss_ws_kernel<11, true, 2>' in n or ('fusion_loss_ws_kernel' in n and '1, 2>' in n)
                or 'fusion_loss_bwd_kernel<11, true, true, false>' in n or ('fusion_loss_bwd_kernel' in n and '1, 1, 0' in n)
                for n in norm), names
     assert any('rescale_unit_kernel' in n for n in names), names
@@ -422,3 +423,32 @@ def test_warp_specialised_kernel_equals_the_two_cta_kernel_on_a_shape_sweep(monk
         for x0, x1, nm in ((u0, u1, 'single-pass'), (d0, d1, 'recomputing')):
             err = (x0 - x1).abs().max().item() / max(x0.abs().max().item(), 1e-30)
             assert err <= 2e-6, ((B, H, W), nm, err)
+
+
+def test_cabi_want_grad_2_writes_the_loss_values_and_the_same_gradient():
+    """want_grad = 2 (what the drop-in modules pass: the training step reads the three loss values only): the same gradient
+    bit for bit, the same loss head and per-sample SSIM means as want_grad = 1, cs / sigma entries written as 0."""
+    L, ML = _mods()
+    lib = L.load()
+    for name in ('rand_3x64x96', 'ir_crop_max'):
+        a, b, f = (T(x).cuda() for x in cases.loss_case(name))
+        B, H, W = a.shape[0], a.shape[2], a.shape[3]
+        st = L.stream_int(a.device)
+        res = {}
+        for wg in (1, 2):
+            cfg = ML._cfg(1.0, 'max', 'max', 'l1', 'l1', 1.0, 0.01, 0.1)
+            cfg.want_grad = wg
+            out = torch.full((lib.mmif_loss_out_doubles(B),), float('nan'), dtype=torch.float64, device='cuda')
+            ws = torch.zeros(lib.mmif_loss_workspace_bytes(B, H, W), dtype=torch.uint8, device='cuda')
+            dU = torch.full_like(f, float('nan'))
+            L.check(lib.mmif_fusion_loss_fwd(a.data_ptr(), b.data_ptr(), f.data_ptr(), B, H, W, ctypes.byref(cfg), out.data_ptr(),
+                                             dU.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            torch.cuda.synchronize()
+            res[wg] = (out[:L.LOSS_HEAD + L.LOSS_PER_SAMPLE * B].clone(), dU.clone())
+        (o1, g1), (o2, g2) = res[1], res[2]
+        assert torch.equal(g1, g2)
+        assert torch.equal(o1[:L.LOSS_HEAD], o2[:L.LOSS_HEAD])
+        p1 = o1[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
+        p2 = o2[L.LOSS_HEAD:].view(B, L.LOSS_PER_SAMPLE)
+        assert torch.equal(p1[:, [0, 3]], p2[:, [0, 3]])                    # ssim means of the two pairs
+        assert (p2[:, [1, 2, 4, 5]] == 0).all() and (p1[:, [1, 2, 4, 5]] != 0).all()
