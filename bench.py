@@ -793,11 +793,16 @@ def metric_suite_leg(dev, MM, world=1):
         for pa, pb, pf in host_pairs:
             eval_py_row(MM, pa, pb, pf)
         per_pair_ms = (time.perf_counter() - t0) / len(host_pairs) * 1e3
-        t0 = time.perf_counter()               # of which: the three pageable host->device copies eval.py's CPU tensors need
+        t0 = time.perf_counter()               # of which: the three host->device copies eval.py's CPU tensors need, as the
+        for pa, pb, pf in host_pairs:          # drop-ins do them (pageable memory through a pinned staging ring)
+            ups = [MM._staged_upload(t, dev) for t in (pa, pb, pf)]
+        torch.cuda.synchronize()
+        upload_ms = (time.perf_counter() - t0) / len(host_pairs) * 1e3
+        t0 = time.perf_counter()               # and what plain tensor.cuda() from pageable memory would cost
         for pa, pb, pf in host_pairs:
             ups = [t.cuda() for t in (pa, pb, pf)]
         torch.cuda.synchronize()
-        upload_ms = (time.perf_counter() - t0) / len(host_pairs) * 1e3
+        upload_plain_ms = (time.perf_counter() - t0) / len(host_pairs) * 1e3
         del ups
         cpu_s = None
         if world == 1:          # under torchrun the other ranks spin on the host cores: a CPU timing there is not a baseline
@@ -827,6 +832,7 @@ def metric_suite_leg(dev, MM, world=1):
                      'e2e_f32_host_pairs_per_s': n / (ms_f32 * 1e-3), 'e2e_u8_host_pairs_per_s': n / (ms_u8 * 1e-3),
                      'h2d_bytes_f32': 12 * n * h * w, 'h2d_bytes_u8': 3 * n * h * w, 'd2h_bytes': n * 16 * 8,
                      'eval_py_call_pattern_ms_per_pair': per_pair_ms, 'eval_py_upload_share_ms_per_pair': upload_ms,
+                     'eval_py_upload_plain_cuda_ms_per_pair': upload_plain_ms,
                      'cpu_reference_pairs_per_s': (1.0 / cpu_s) if cpu_s else None, 'cpu_cores': torch.get_num_threads() if cpu_s else None,
                      'cpu_sample': ('1 pair, single run: ' + cpu_kind) if cpu_s else 'not timed under torchrun (N > 1)'}
         if ms_sub is not None:      # BASELINE configs[3]: MS-SSIM + VIFF + Qabf only (51.6 algorithmic B/px)
