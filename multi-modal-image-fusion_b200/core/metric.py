@@ -68,7 +68,9 @@ class _PinnedStage:
 
     def upload(self, t, device):
         nbytes = t.numel() * t.element_size()
-        if t.is_pinned() or nbytes < (64 << 10) or nbytes > (256 << 20) or t.is_sparse or t.layout != torch.strided:
+        # (with one host thread — torchrun sets OMP_NUM_THREADS=1 — the host copy is no faster than the driver's own staging)
+        if (t.is_pinned() or nbytes < (64 << 10) or nbytes > (256 << 20) or t.is_sparse or t.layout != torch.strided
+                or torch.get_num_threads() < 4):
             return t.to(device, non_blocking=False)
         with self.lock:
             k = self.k
