@@ -20,8 +20,8 @@
 //     port turned out to be the binding resource (a packed FFMA2 holds it for two cycles: issue 62 % + packed shadows 30 %
 //     = 92-94 % busy), so the hand-overs between groups are HARDWARE named barriers (bar.arrive / bar.sync: a blocked warp
 //     issues nothing) and only the TMA ring keeps mbarriers;
-//   * with the port saturated the only remaining lever is the instruction count per batch (2.86 k per 8 x 128 tile now).
-// Shared memory (218 KB of the SM's 227): 7-slot input ring (G3's combine reads rows three batches behind G0's prefetch),
+//   * with the port saturated the only remaining lever is the instruction count per batch (2.73 k per 8 x 128 tile now).
+// Shared memory (213 KB of the SM's 227): 7-slot input ring (G3's combine reads rows three batches behind G0's prefetch),
 // double-buffered vbuf / cbuf / gbuf, one tbuf.
 #pragma once
 
@@ -46,7 +46,7 @@ constexpr unsigned kWsSleepNs = MMIF_WS_SLEEP_NS;
 constexpr int kWsGroupBytes = 3 * kRB * kRPB * 4;
 
 struct SmemWS {
-    float ring[3][kWsRows][kRPB];                      // 76032 B
+    float ring[3][kWsRows][kRPB];                      // 88704 B
     alignas(16) float2 vbuf[2][kRB * kVPitch];         // 2 x 34944 B
     alignas(16) float2 cbuf[2][kRB * kCPitch];         // 2 x 16512 B
     alignas(16) float2 tbuf[kRB * kCPitch];            // 16512 B
@@ -64,14 +64,14 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Wait with a suspend-time hint (the waiting warp sleeps in hardware until the phase completes: a spinning try_wait loop
-// was measured to execute HALF of the kernel's instructions and to starve the working warps of issue slots and
-// instruction fetches) and a watchdog: a protocol error traps (the launch fails) instead of hanging the GPU.
 // Every thread arrives (the plain-load ring: each thread publishes its own stores; also what compute-sanitizer's racecheck
 // can follow).
 __device__ __forceinline__ void mbar_arrive_each(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Poll with a real sleep between the tests and a watchdog (a protocol error traps: the launch fails instead of hanging the
+// GPU).  Only the TMA ring is waited on this way; try_wait's own suspend returned after ~100 cycles and the polling loops of
+// the first version executed 40 % of all instructions, hence named barriers everywhere else.
 __device__ __forceinline__ void mbar_wait_wd(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok = 0;
