@@ -811,8 +811,11 @@ static int launch_bwd(const float* i1, const float* i2, const float* f, int B, i
     // (the other combine / norm modes run the general Sobel path with two norm derivatives per pixel on every batch; that makes
     // the Sobel group the longest pipeline stage: measured 22.6 vs 20.9 ms at 64x3072x4096, 2.79 vs 2.73 ms at 8x — although
     // 58 vs 65 us at 1x1024x1224 — so they stay on the 2-CTA kernel; MMIF_WS_ALL_MODES=1 puts them on the warp-specialised one)
-    static const bool ws_all_modes = getenv("MMIF_WS_ALL_MODES") != nullptr;      // measurement aid
-    const bool use_ws = !ex && win == WIN11 && (fast || ws_all_modes) && !ws_off;
+    // ... at LARGE shapes; up to ~16 Mpix per launch the warp-specialised kernel wins there too (avg + l2: 36 vs 48 us at 2x512x512,
+    // 0.491 vs 0.529 ms at 4x2048x2048), so those modes take it up to 32 Mpix.  MMIF_WS_ALL_MODES=1 forces it at any size.
+    static const bool ws_all_modes = getenv("MMIF_WS_ALL_MODES") != nullptr;
+    const bool small_enough = (long long)B * H * W <= (32ll << 20);
+    const bool use_ws = !ex && win == WIN11 && (fast || ws_all_modes || small_enough) && !ws_off;
     const BwdGeom g = bwd_geom(B, H, W, win, use_ws);
     BwdParams p;
     memset(&p, 0, sizeof(p));

@@ -25,6 +25,8 @@ for (B, H, W) in ((2, 96, 352), (1, 70, 131)):          # 352: 4 strips, interio
     torch.autograd.grad(2.0 * l1 + l3, f)                 # recomputing backward
     with torch.no_grad():
         ML.SSIMLoss('ssim')(a, b, f.detach()).item()      # forward-only kernel
+    f3 = f.detach().clone().requires_grad_(True)          # avg / l2 modes: the general instantiation of the warp-specialised kernel
+    (ML.SSIMLoss('ssim')(a, b, f3) + ML.PixelLoss('l2', 0.01)(a, b, f3, mode='avg') + ML.GradLoss('l2', 0.1)(a, b, f3, mode='avg')).backward()
     f2 = f.detach().clone().requires_grad_(True)
     ML.SSIMLoss('ms-ssim')(torch.rand(1, 1, 192, 208, generator=g).cuda(), torch.rand(1, 1, 192, 208, generator=g).cuda(),
                            torch.rand(1, 1, 192, 208, generator=g).cuda().requires_grad_(True)).backward()
