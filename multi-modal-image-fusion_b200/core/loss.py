@@ -2,10 +2,12 @@
 
 Same class names, constructor arguments, ``forward`` signatures, return types and error
 behaviour as the reference (loss.py:16-19); the arithmetic runs in libmmif_b200.so.  The three
-training modules share ONE fused forward launch and ONE backward launch per step: the first of
-``SSIMLoss / PixelLoss / GradLoss`` called on a new (img1, img2, imgf) triple launches the fused
-kernel, the other two read their scalar from the same result (memo keyed on tensor identity and
-version), and a single autograd node with three outputs receives all three upstream gradients.
+training modules share ONE launch per step: the first of ``SSIMLoss / PixelLoss / GradLoss`` called on a
+new (img1, img2, imgf) triple launches the single-pass kernel (the three loss values AND
+d(l1 + l2 + l3)/d imgf when imgf wants a gradient; the forward-only kernel otherwise), the other two read
+their scalar from the same result (memo keyed on tensor identity and version), and a single autograd node
+with three outputs receives all three upstream gradients: ``total.backward()`` is an in-place rescale that
+exits at once for unit upstream; unequal upstream gradients or a retained graph recompute.
 
 Built on the same kernels: 'w-ssim' (per-sample gamma weights in the backward kernel), 'ms-ssim'
 (one SSIM forward/backward launch per pyramid level + pooling adjoints), use_padding=True (reflect-pad
